@@ -1,0 +1,46 @@
+"""Host-side camera algebra of the path (tiny 4x4 work; stays in PyTorch by design).
+
+The kernels take 12 floats per (view, batch item): the 3x3 `rot` (row-major) and the
+3-vector `trans` of   proj = src_proj @ inverse(ref_proj)   exactly as the reference
+forms them (models/module.py:295-297), from projections composed the way
+DepthNet.forward does (models/TransMVSNet.py:75-78).  They are computed with the same
+torch ops as the reference so the kernels see bit-identical matrices.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+
+def compose_projection(proj_pair: torch.Tensor) -> torch.Tensor:
+    """[B,2,4,4] (extrinsic, intrinsic) -> [B,4,4] with the top 3x4 = K[:3,:3] @ E[:3,:4].
+
+    Mirrors models/TransMVSNet.py:75-76.
+    """
+    out = proj_pair[:, 0].clone()
+    out[:, :3, :4] = torch.matmul(proj_pair[:, 1, :3, :3], proj_pair[:, 0, :3, :4])
+    return out
+
+
+def relative_rot_trans(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> torch.Tensor:
+    """[B,4,4] x2 -> [B,12] = (rot row-major, trans) of src_proj @ inverse(ref_proj).
+
+    Mirrors models/module.py:295-297.
+    """
+    proj = torch.matmul(src_proj, torch.inverse(ref_proj))
+    rot = proj[:, :3, :3].reshape(-1, 9)
+    trans = proj[:, :3, 3]
+    return torch.cat([rot, trans], dim=1).contiguous()
+
+
+def stage_rot_trans(proj_matrix: torch.Tensor) -> torch.Tensor:
+    """proj_matrix [B,N,2,4,4] -> [Nsrc,B,12] for every source view against view 0.
+
+    The 4x4 algebra runs on the CPU (the matrices come from the host dataset and are a few
+    hundred bytes); the result is passed to the kernels by value.
+    """
+    pm = proj_matrix.detach().to("cpu", torch.float32)
+    views = torch.unbind(pm, 1)
+    ref = compose_projection(views[0])
+    return torch.stack([relative_rot_trans(compose_projection(v), ref) for v in views[1:]], 0)

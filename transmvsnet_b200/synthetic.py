@@ -1,0 +1,162 @@
+"""Seeded synthetic inputs for the cost-volume path.
+
+Shapes and units mimic what the reference's datasets feed the path
+(datasets/general_eval.py:66-98,185-209 for the camera/proj_matrix format and
+depth_values; models/TransMVSNet.py:113-132 for the (C, D, scale) of each stage;
+models/module.py:606-634 for the per-pixel depth hypotheses).  Everything is made
+on the CPU with a torch.Generator so the same tensors can be rebuilt on any box.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+# (channels, depth planes, downscale) per cascade stage: models/module.py:397,
+# models/TransMVSNet.py:113-132
+STAGES = ((32, 48, 4), (16, 32, 2), (8, 8, 1))
+DEPTH_RATIOS = (4.0, 1.0, 0.5)  # models/TransMVSNet.py:114 depth_interals_ratio
+
+# DTU camera (datasets/general_eval.py:73-76) at the 1600x1200 capture size
+_DTU_FX, _DTU_FY, _DTU_CX, _DTU_CY = 2892.33, 2883.18, 823.205, 619.071
+
+
+@dataclass
+class StageInputs:
+    """One cascade stage of one batch of reference views."""
+    stage: int
+    features: List[torch.Tensor]          # N x [B,C,h,w], features[0] is the reference view
+    proj_matrix: torch.Tensor             # [B,N,2,4,4]  ([...,0]=extrinsic, [...,1,:3,:3]=intrinsic)
+    depth_values: torch.Tensor            # [B,D,h,w] per-pixel hypotheses
+    view_weights: torch.Tensor            # [B,Nsrc,h,w]
+    logits: torch.Tensor                  # [B,D,h,w] stand-in for the 3-D CNN output
+    num_depth: int = 0
+
+    @property
+    def voxel_views(self) -> int:
+        b, d, h, w = self.depth_values.shape
+        return b * d * h * w * (len(self.features) - 1)
+
+
+def _look_at_extrinsic(center: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """World-to-camera 4x4 for a camera at `center` whose optical axis passes through `target`."""
+    z = target - center
+    z = z / z.norm()
+    up = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64)
+    x = torch.linalg.cross(up, z)
+    x = x / x.norm()
+    y = torch.linalg.cross(z, x)
+    rot = torch.stack([x, y, z])          # rows = camera axes in world coords
+    ext = torch.eye(4, dtype=torch.float64)
+    ext[:3, :3] = rot
+    ext[:3, 3] = -rot @ center
+    return ext
+
+
+def make_cameras(batch: int, n_views: int, height: int, width: int, *, kind: str = "dtu",
+                 seed: int = 0) -> Dict[str, torch.Tensor]:
+    """proj_matrix per stage, in the reference's [B,N,2,4,4] format, plus depth_values[B,192].
+
+    kind "dtu": DTU intrinsics rescaled to (height, width), depth 425 + 2.5*k mm, sources on
+    50-150 mm baselines converging at z=680 mm (3-13 degrees).  kind "unit": fx=fy=0.6*W,
+    depth range [0.5, 10] scene units (Tanks&Temples / BlendedMVS shaped).
+    """
+    g = torch.Generator().manual_seed(seed + 7919)
+    if kind == "dtu":
+        fx = _DTU_FX * width / 1600.0
+        fy = _DTU_FY * height / 1200.0
+        cx = _DTU_CX * width / 1600.0
+        cy = _DTU_CY * height / 1200.0
+        d_min, d_int, focus = 425.0, 2.5, 680.0
+        base_lo, base_hi = 50.0, 150.0
+    elif kind == "unit":
+        fx = fy = 0.6 * width
+        cx, cy = 0.5 * width, 0.5 * height
+        d_min, d_int, focus = 0.5, 9.5 / 191.0, 3.0
+        base_lo, base_hi = 0.2, 0.6
+    else:
+        raise ValueError(kind)
+    k_full = torch.tensor([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    depth_values = (d_min + d_int * torch.arange(192, dtype=torch.float64)).float()
+    depth_values = depth_values[None].repeat(batch, 1)
+
+    proj = {}
+    ext_all = torch.zeros(batch, n_views, 4, 4, dtype=torch.float64)
+    for b in range(batch):
+        for v in range(n_views):
+            if v == 0:
+                ext_all[b, v] = torch.eye(4, dtype=torch.float64)
+                continue
+            ang = 2.0 * math.pi * (v - 1) / max(n_views - 1, 1) + 0.3 + 0.37 * b
+            mag = base_lo + (base_hi - base_lo) * float(torch.rand((), generator=g))
+            center = torch.tensor([mag * math.cos(ang), mag * math.sin(ang), 0.0], dtype=torch.float64)
+            target = torch.tensor([0.0, 0.0, focus], dtype=torch.float64)
+            ext_all[b, v] = _look_at_extrinsic(center, target)
+    for s, (_, _, scale) in enumerate(STAGES, start=1):
+        k = k_full.clone()
+        k[:2, :] = k[:2, :] / scale
+        pm = torch.zeros(batch, n_views, 2, 4, 4, dtype=torch.float32)
+        pm[:, :, 0] = ext_all.float()
+        pm[:, :, 1, :3, :3] = k.float()
+        proj[f"stage{s}"] = pm
+    proj["depth_values"] = depth_values
+    return proj
+
+
+def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 1152, width: int = 1600,
+               kind: str = "dtu", seed: int = 0, channels: Optional[int] = None,
+               num_depth: Optional[int] = None, cameras: Optional[Dict[str, torch.Tensor]] = None,
+               stage1_weights: Optional[torch.Tensor] = None) -> StageInputs:
+    """Synthetic inputs of cascade stage `stage` (1..3) for an image of (height, width)."""
+    c_def, d_def, scale = STAGES[stage - 1]
+    c = channels or c_def
+    d = num_depth or d_def
+    h, w = height // scale, width // scale
+    g = torch.Generator().manual_seed(seed * 1000 + stage)
+    cams = cameras or make_cameras(batch, n_views, height, width, kind=kind, seed=seed)
+    dv = cams["depth_values"]                                # [B,192]
+    d_min, d_max = dv[:, 0], dv[:, -1]
+    depth_interval = (d_max - d_min) / dv.shape[1]           # models/TransMVSNet.py:149
+    if stage == 1:
+        # models/module.py:616-623 (2-D branch): the global range split into D planes
+        new_int = (d_max - d_min) / (d - 1)
+        hyp = d_min[:, None] + torch.arange(d, dtype=torch.float32)[None] * new_int[:, None]
+        hyp = hyp[:, :, None, None].expand(batch, d, h, w).contiguous()
+    else:
+        # smooth surface in roughly the middle 70% of the range, then module.py:626-632
+        yy = torch.linspace(0, 1, h)[:, None]
+        xx = torch.linspace(0, 1, w)[None, :]
+        span = (d_max - d_min)[:, None, None]
+        mid = (d_min + 0.5 * (d_max - d_min))[:, None, None]
+        surf = mid + 0.25 * span * torch.sin(3.0 * math.pi * xx) * torch.cos(2.0 * math.pi * yy)[None] \
+            + 0.1 * span * (xx - 0.5)[None]
+        ipx = (DEPTH_RATIOS[stage - 1] * depth_interval)[:, None, None]
+        cur_min = surf - d / 2 * ipx
+        cur_max = surf + d / 2 * ipx
+        new_int = (cur_max - cur_min) / (d - 1)
+        hyp = cur_min[:, None] + torch.arange(d, dtype=torch.float32)[None, :, None, None] * new_int[:, None]
+        hyp = hyp.contiguous()
+    feats = [torch.randn(batch, c, h, w, generator=g) for _ in range(n_views)]
+    if stage1_weights is None:
+        h1, w1 = height // STAGES[0][2], width // STAGES[0][2]
+        gw = torch.Generator().manual_seed(seed * 1000 + 17)
+        stage1_weights = torch.sigmoid(torch.randn(batch, n_views - 1, h1, w1, generator=gw))
+    vw = stage1_weights
+    for _ in range(stage - 1):                               # models/TransMVSNet.py:193-194
+        vw = torch.nn.functional.interpolate(vw, scale_factor=2, mode="nearest")
+    if vw.shape[2] < h or vw.shape[3] < w:                   # sizes not divisible by the stage scales
+        vw = torch.sigmoid(torch.randn(batch, n_views - 1, h, w, generator=g))
+    vw = vw[:, :, :h, :w].contiguous()
+    logits = 3.0 * torch.randn(batch, d, h, w, generator=g)
+    return StageInputs(stage=stage, features=feats, proj_matrix=cams[f"stage{stage}"],
+                       depth_values=hyp.float(), view_weights=vw, logits=logits, num_depth=d)
+
+
+def make_cascade(*, batch: int = 1, n_views: int = 5, height: int = 1152, width: int = 1600,
+                 kind: str = "dtu", seed: int = 0) -> List[StageInputs]:
+    """All three stages of one batch of reference views (BASELINE.json configs 2-4)."""
+    cams = make_cameras(batch, n_views, height, width, kind=kind, seed=seed)
+    return [make_stage(s, batch=batch, n_views=n_views, height=height, width=width, kind=kind,
+                       seed=seed, cameras=cams) for s in (1, 2, 3)]
