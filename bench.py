@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the TransMVSNet cost-volume hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl tmvs|reference] [--workload dtu|tnt|bld]
+
+A "step" is one pass of the hot path over ONE reference view of the named cascade: for each of
+the three stages  pack sources -> fused cost volume (warp+sample+correlate+aggregate) -> softmax/WTA
+read-out  = 9 kernel launches.  metric = cost-volume voxel-views/s (D*h*w*Nsrc summed over the stages,
+BASELINE.json) and ms per reference view.  Under torchrun every rank processes its own reference
+views (weak scaling, sharded by reference view) and the stage-3 depth/confidence maps are gathered
+on rank 0 over NCCL.
+
+--impl reference times the reference's PyTorch CPU op sequence (oracle/torch_port.py: the reference is
+Python and /root/reference does not exist on the GPU box) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: DTU test cascade 1152x1600, N=5, depths 48/32/8
+    "dtu": dict(height=1152, width=1600, n_views=5, kind="dtu", batch=1,
+                name="DTU 1152x1600 N=5 D=48/32/8 C=32/16/8 fp32 forward, 1 reference view per step"),
+    # configs[2]: Tanks&Temples-shaped 1920x1056, N=7
+    "tnt": dict(height=1056, width=1920, n_views=7, kind="unit", batch=1,
+                name="T&T-shaped 1056x1920 N=7 D=48/32/8 fp32 forward, 1 reference view per step"),
+    # configs[3] forward part: BlendedMVS-shaped 768x576, N=7, batch 8
+    "bld": dict(height=576, width=768, n_views=7, kind="unit", batch=8,
+                name="BlendedMVS-shaped 576x768 N=7 B=8 D=48/32/8 fp32 forward"),
+}
+CPU_SAMPLE_DIV = 4      # the CPU arms run the same cascade on an image 1/4 x 1/4 the size (1/16 of the voxels)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tmvs", choices=["tmvs", "reference"])
+    ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def voxel_views(stages) -> int:
+    return sum(s.voxel_views for s in stages)
+
+
+def algorithmic_bytes(st) -> dict:
+    """SURVEY.md 8(d) per-stage algorithmic bytes (fp32) for the three kernels of one stage."""
+    b, d, h, w = st.depth_values.shape
+    n_src = len(st.features) - 1
+    c = st.features[0].shape[1]
+    hw = h * w
+    return {
+        # read Nsrc*C*h*w NCHW, write the same packed
+        "pack_sources": 4 * b * (2 * n_src * c * hw),
+        # (1+Nsrc)*C*h*w features + D*h*w hypotheses + Nsrc*h*w weights in, D*h*w similarity out
+        "costvol_fwd": 4 * b * ((1 + n_src) * c * hw + d * hw + n_src * hw + d * hw),
+        # logits + hypotheses in, prob out, index(int64)+depth+conf out
+        "softmax_wta": 4 * b * (3 * d * hw + 4 * hw),
+    }
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while `active` is set."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.active, self.stop_flag = index, threading.Event(), threading.Event()
+        self.sm, self.mask, self.sm_max, self.err = [], 0, None, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                if self.active.is_set():
+                    self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    self.mask |= int(get_reasons(h))
+                time.sleep(0.002)
+        except Exception as e:          # noqa: BLE001 -- the clocks record is best effort, never fatal
+            self.err = repr(e)
+
+    def summary(self) -> dict:
+        reasons = [n for bit, n in self.REASONS.items() if self.mask & bit]
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(self.sm), **({"error": self.err} if self.err else {})}
+
+
+# ----------------------------------------------------------------------------------------- CPU arms
+def cpu_hot_path_time(workload: dict, steps: int, warmup: int):
+    """The reference's PyTorch CPU op sequence (oracle/torch_port.py) on a bounded sample of the workload."""
+    import torch
+    from oracle import torch_port
+    from transmvsnet_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = workload["height"] // CPU_SAMPLE_DIV, workload["width"] // CPU_SAMPLE_DIV
+    h, w = h // 4 * 4, w // 4 * 4
+    stages = synthetic.make_cascade(batch=1, n_views=workload["n_views"], height=h, width=w, kind=workload["kind"], seed=0)
+    vv = voxel_views(stages)
+    with torch.no_grad():
+        for _ in range(warmup):
+            for st in stages:
+                torch_port.hot_path(st)
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            for st in stages:
+                torch_port.hot_path(st)
+            times.append(time.perf_counter() - t0)
+    sample = (f"same cascade on a {h}x{w} image (1/{CPU_SAMPLE_DIV ** 2} of the voxels), N={workload['n_views']}, "
+              f"{vv / 1e6:.2f} M voxel-views per step, torch {torch.__version__} CPU ops, view weights given")
+    return vv, times, cores, sample
+
+
+def run_reference_arm(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))          # bounded: each step is seconds of CPU work
+    warmup = 1 if args.warmup > 0 else 0
+    vv, times, cores, sample = cpu_hot_path_time(workload, steps, warmup)
+    total = sum(times)
+    value = vv * len(times) / total
+    line = {
+        "impl": "reference", "metric": "cost_volume_voxel_views_per_s", "value": value, "unit": "voxel-views/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload["name"], "timed_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "voxel-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "requested_steps": args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_tmvs_arm(args, workload):
+    import torch
+    import torch.distributed as dist
+    from transmvsnet_b200 import _lib, ops, pipeline, sharding, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl tmvs needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    host = [pipeline.pin_stage(s) for s in synthetic.make_cascade(
+        batch=workload["batch"], n_views=workload["n_views"], height=workload["height"], width=workload["width"],
+        kind=workload["kind"], seed=rank)]
+    dev_stages = [pipeline.stage_to_device(s, dev) for s in host]
+    vv = voxel_views(host)
+    torch.cuda.synchronize()
+    comm = torch.cuda.Stream() if world > 1 else None
+
+    def step():
+        outs = pipeline.run_cascade(dev_stages)
+        if world > 1:       # gather this view's stage-3 depth + confidence on rank 0, off the compute stream
+            maps = torch.stack([outs[-1]["depth"], outs[-1]["photo_confidence"]], 1)    # [B,2,H,W]
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                maps.record_stream(comm)
+                sharding.gather_maps(maps, maps.shape[0] * world)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- device-resident throughput: exactly K steps, CUDA events on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.LAUNCHES
+    sampler.active.set()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    if comm is not None:
+        torch.cuda.current_stream().wait_stream(comm)
+    e1.record()
+    barrier()
+    sampler.active.clear()
+    launches = _lib.LAUNCHES - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * vv * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events around each launch, same stream), for the roofline block
+    names = ["pack_sources", "costvol_fwd", "softmax_wta"]
+    reps = max(3, min(args.steps, 20))
+    dur = {(s, n): 0.0 for s in range(3) for n in names}
+    evs = []
+    sampler.active.set()
+    for _ in range(reps):
+        for si, d in enumerate(dev_stages):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            packed = ops.pack_sources(d["features"][1:])
+            ev[1].record()
+            ops.cost_volume_packed(d["features"][0], packed, d["rot_trans"], d["depth_values"], d["view_weights"], False, True)
+            ev[2].record()
+            ops.softmax_wta(d["logits"], d["depth_values"])
+            ev[3].record()
+            evs.append((si, ev))
+    torch.cuda.synchronize()
+    sampler.active.clear()
+    for si, ev in evs:
+        for k, n in enumerate(names):
+            dur[(si, n)] += ev[k].elapsed_time(ev[k + 1]) / reps
+    kernels = []
+    for si, st in enumerate(host):
+        ab = algorithmic_bytes(st)
+        for n in names:
+            ms = dur[(si, n)]
+            kernels.append({"kernel": f"{n}/stage{si + 1}", "ms": round(ms, 4), "algorithmic_mb": round(ab[n] / 1e6, 2),
+                            "gbps": round(ab[n] / 1e9 / (ms * 1e-3), 1) if ms > 0 else None})
+    top = max(kernels, key=lambda k: k["ms"])
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    traffic = None
+    tr_path = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(top["kernel"])
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s",
+                "frac": round(top["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": top["ms"], "algorithmic_bytes": int(top["algorithmic_mb"] * 1e6),
+                "all_kernels": kernels,
+                "step_algorithmic_frac": round(sum(k["algorithmic_mb"] for k in kernels) * 1e6 / 1e9 /
+                                               (elapsed_ms * 1e-3 / args.steps) / peak, 4)}
+
+    # ---- end to end through the public API: pinned host inputs, H2D + kernels + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        pipe = pipeline.HostPipeline(dev)
+        for _ in range(2):
+            pipe.process_view(host)
+        barrier()
+        k_e2e = max(1, min(args.steps, 20))
+        sampler.active.set()
+        e0.record()
+        for _ in range(k_e2e):
+            pipe.process_view(host)
+        e1.record()
+        barrier()
+        sampler.active.clear()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        e2e = {"value": world * vv * k_e2e / (ms * 1e-3), "unit": "voxel-views/s",
+               "h2d_bytes_per_step": sum(pipeline.stage_h2d_bytes(s) for s in host),
+               "d2h_bytes_per_step": pipeline.HostPipeline.d2h_bytes(host), "steps": k_e2e,
+               "ms_per_step": ms / k_e2e}
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cvv, times, cores, sample = cpu_hot_path_time(workload, steps=2, warmup=1)
+        cpu = {"value": cvv / min(times), "unit": "voxel-views/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "cost_volume_voxel_views_per_s", "value": value, "unit": "voxel-views/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+            "ms_per_ref_view": elapsed_ms / args.steps / workload["batch"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload["name"], "voxel_views_per_step": vv,
+                       "l2": "inputs larger than L2 (>= 1 GB touched per step)", "view_weights": "given as inputs",
+                       "sharding": "by reference view, one process per GPU" + (", NCCL all_gather of depth+conf" if world > 1 else "")},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    workload = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, workload)
+    else:
+        run_tmvs_arm(args, workload)
+
+
+if __name__ == "__main__":
+    main()

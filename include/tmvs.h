@@ -1,0 +1,136 @@
+/*
+ * tmvs.h -- C ABI of libtmvs_sm100a.so: B200 (sm_100a) kernels for the TransMVSNet
+ * cost-volume hot path.
+ *
+ * The reference has NO plugin / operator / FFI boundary for this path: the "interface" is two
+ * plain Python functions bound by a star import (models/TransMVSNet.py:4) and the statements
+ * of DepthNet.forward between them.  Each entry point below names the reference lines it
+ * replaces; INTEGRATION.md shows the ctypes stub that binds it from the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless it says "host"; the library never
+ *     allocates, frees or retains memory (PyTorch owns all buffers) and never synchronises;
+ *   - launches go to `stream` (a cudaStream_t / CUstream passed as void*), current device;
+ *   - returns 0 on success, a negative TMVS_E_* code for argument errors, or a positive
+ *     cudaError_t if a launch failed; tmvs_error_string() describes either;
+ *   - tensors are contiguous in the layouts written beside them; feature inputs additionally
+ *     take element strides so NCHW and torch.channels_last tensors are both accepted;
+ *   - "packed" source features use the kernel-native blocked channel-last layout
+ *       [Nsrc][B][C4][H][W][4],  C4 = ceil(C/4), zero padded,
+ *     produced by tmvs_pack_sources(): one bilinear tap of 4 channels is one 128-bit load and
+ *     x-adjacent pixels are adjacent in memory;
+ *   - rot_trans is a HOST array [Nsrc][B][12]: 3x3 `rot` (row major) then `trans` of
+ *       proj = src_proj @ inverse(ref_proj)            (models/module.py:295-297),
+ *     computed by the caller with the same torch ops as the reference;
+ *   - depth hypotheses are [B][D] (per_pixel = 0) or [B][D][H][W] (per_pixel = 1), the two
+ *     shapes models/module.py:288,306 accepts.
+ */
+#ifndef TMVS_H_
+#define TMVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMVS_VERSION 100          /* 0.1.0 */
+#define TMVS_MAX_SRC_VIEWS 16     /* source views per launch */
+#define TMVS_MAX_DEPTH 256        /* depth planes per pixel */
+
+enum {
+    TMVS_OK = 0,
+    TMVS_E_NULL = -1,        /* a required pointer is NULL */
+    TMVS_E_SHAPE = -2,       /* a dimension is <= 0 or above a TMVS_MAX_* limit */
+    TMVS_E_ALIGN = -3,       /* a packed / vector pointer is not 16-byte aligned */
+    TMVS_E_UNSUPPORTED = -4  /* combination not implemented */
+};
+
+typedef void *tmvs_stream_t;
+
+int tmvs_version(void);
+const char *tmvs_error_string(int code);
+
+/* Bytes of the packed source workspace for the given shape. */
+size_t tmvs_packed_bytes(int n_src, int B, int C, int H, int W);
+
+/*
+ * Layout pre-pass: the N source feature maps  ->  packed [Nsrc][B][C4][H][W][4].
+ * src[i] points at view i's [B,C,H,W] tensor with element strides (sB,sC,sH,sW), so the
+ * NCHW output of the reference's FeatureNet/FMT (models/module.py:399-422, models/FMT.py:212-230)
+ * and channels_last tensors are both read in place.   src is a HOST array of device pointers.
+ */
+int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
+                      float *packed, int B, int C, int H, int W, tmvs_stream_t stream);
+
+/*
+ * Drop-in homo_warping (models/module.py:284-322) for ONE source view: materialises the
+ * warped volume out[B][C][D][H][W].  packed_view = this view's slice [B][C4][H][W][4];
+ * rot_trans = host [B][12].
+ */
+int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const float *depth, int per_pixel,
+                       float *out, int B, int C, int D, int H, int W, tmvs_stream_t stream);
+
+/*
+ * Fused warp + bilinear sampling + correlation (+ view-weighted aggregation):
+ * replaces the whole view loop models/TransMVSNet.py:71-93 (homo_warping :79,
+ * (warped*ref).mean(1) :80, similarity_sum/weight_sum :88-93) without ever writing the
+ * B x C x D x H x W warped volume.
+ *   ref            reference features [B,C,H,W] with element strides (rB,rC,rH,rW)
+ *   packed         packed sources [Nsrc][B][C4][H][W][4]
+ *   view_weights   [B][Nsrc][H][W] or NULL
+ *   sim_views      [Nsrc][B][D][H][W] per-view similarity (stage 1, feeds PixelwiseNet) or NULL
+ *   agg            [B][D][H][W] = sum_i sim_i*w_i / (1e-5 + sum_i w_i)  or NULL (needs view_weights)
+ */
+int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                     const float *packed, const float *rot_trans, const float *depth, int per_pixel,
+                     const float *view_weights, float *sim_views, float *agg,
+                     int B, int C, int D, int H, int W, int n_src, tmvs_stream_t stream);
+
+/*
+ * Aggregation alone (stage 1 after PixelwiseNet, models/TransMVSNet.py:71-72,88-93):
+ * agg[B][D][H][W] = sum_i sim_views[i]*w[:,i] / (1e-5 + sum_i w[:,i]).
+ */
+int tmvs_aggregate_fwd(const float *sim_views, const float *view_weights, float *agg,
+                       int B, int D, int H, int W, int n_src, tmvs_stream_t stream);
+
+/*
+ * Backward of the cost volume wrt the features (autograd of models/module.py:318-320 and
+ * models/TransMVSNet.py:80).  grad_views = dL/d sim_i [Nsrc][B][D][H][W].
+ *   grad_ref  [B][C][H][W]            (contiguous NCHW, overwritten)
+ *   grad_src  [Nsrc][B][C][H][W]      (contiguous NCHW, overwritten)
+ * Deterministic and free of floating-point atomics.  Either output may be NULL.
+ */
+int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                     const float *packed, const float *rot_trans, const float *depth, int per_pixel,
+                     const float *grad_views, float *grad_ref, float *grad_src, void *workspace,
+                     size_t workspace_bytes, int B, int C, int D, int H, int W, int n_src,
+                     tmvs_stream_t stream);
+size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src);
+
+/*
+ * Read-out (models/TransMVSNet.py:99-103 + models/module.py:474-482) in one pass:
+ *   prob = exp(log_softmax(logits, dim=1)); index = argmax_d prob (first maximal, int64);
+ *   depth = depth_values[index]; conf = max_d prob.      prob may be NULL (not materialised).
+ */
+int tmvs_softmax_wta_fwd(const float *logits, const float *depth_values, float *prob, int64_t *index,
+                         float *depth, float *conf, int B, int D, int H, int W, tmvs_stream_t stream);
+
+/* depth_wta(p, depth_values) (models/module.py:474-482): index (int64, may be NULL) + depth. */
+int tmvs_depth_wta(const float *p, const float *depth_values, int64_t *index, float *depth,
+                   int B, int D, int H, int W, tmvs_stream_t stream);
+
+/*
+ * depth_regression(p, depth_values) = sum_d p*depth_values.  ABSENT from this fork of the
+ * reference (north_star signature, upstream MVSNet definition).
+ * bwd: grad_p[B][D][H][W] = grad_depth[B][H][W] * depth_values.
+ */
+int tmvs_depth_regression_fwd(const float *p, const float *depth_values, int per_pixel, float *depth,
+                              int B, int D, int H, int W, tmvs_stream_t stream);
+int tmvs_depth_regression_bwd(const float *grad_depth, const float *depth_values, int per_pixel,
+                              float *grad_p, int B, int D, int H, int W, tmvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMVS_H_ */

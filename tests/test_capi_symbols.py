@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol include/tmvs.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from conftest import REPO
+from transmvsnet_b200 import _lib
+
+
+def _declared():
+    text = open(os.path.join(REPO, "include", "tmvs.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tmvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported():
+    names = _declared()
+    assert len(names) >= 12
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/tmvs.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names       # the ctypes table covers the header exactly
+
+
+def test_exports_are_plain_c():
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for n in _declared():
+        assert n in exported                       # unmangled => extern "C"
+
+
+def test_version_and_error_strings():
+    lib = _lib.load()
+    assert lib.tmvs_version() == 100
+    assert lib.tmvs_error_string(0) == b"ok"
+    assert b"NULL" in lib.tmvs_error_string(-1)
+    assert lib.tmvs_packed_bytes(4, 1, 32, 288, 400) == 4 * 8 * 288 * 400 * 16
+    assert lib.tmvs_packed_bytes(4, 1, 30, 2, 2) == 4 * 8 * 4 * 16          # C padded to a multiple of 4
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected before any CUDA call (so this is safe on a CPU-only box)."""
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)
+    assert lib.tmvs_softmax_wta_fwd(null, null, null, null, null, null, 1, 8, 4, 4, null) == -1
+    assert lib.tmvs_softmax_wta_fwd(one, one, null, one, one, one, 1, 0, 4, 4, null) == -2
+    assert lib.tmvs_softmax_wta_fwd(one, one, null, one, one, one, 1, 1000, 4, 4, null) == -2
+    assert lib.tmvs_costvol_fwd(null, 0, 0, 0, 0, null, null, null, 1, null, null, null, 1, 8, 8, 4, 4, 2, null) == -1
+    assert lib.tmvs_costvol_fwd(one, 0, 0, 0, 0, one, one, one, 1, null, one, null, 1, 8, 8, 4, 4, 99, null) == -2
+    assert lib.tmvs_costvol_fwd(one, 0, 0, 0, 0, ctypes.c_void_p(20), one, one, 1, null, one, null,
+                                1, 8, 8, 4, 4, 2, null) == -3
+    assert lib.tmvs_depth_wta(one, one, null, null, 1, 8, 4, 4, null) == -1

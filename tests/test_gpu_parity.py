@@ -1,0 +1,235 @@
+"""Parity of the sm_100a kernels (through the C ABI) with the reference's golden outputs and the oracle.
+
+Run on the B200 box:  python -m pytest tests -m gpu
+Tolerances are the ones in conftest.py (north_star): 1e-4 relative for cost volumes, 1e-3 of the depth
+range for depths, bit-exact integer indices.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import (COSTVOL_REL, DEPTH_FRAC, DEPTHNET_GIVEN, PROB_ABS, WARP_CASES, assert_costvol_close, golden,
+                      rel_err)
+import transmvsnet_b200 as tm
+from transmvsnet_b200 import geometry, ops, synthetic
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.as_tensor(a).to(DEV)
+
+
+# ----------------------------------------------------------------------------- drop-in homo_warping
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_homo_warping_golden(name):
+    g = golden(name)
+    out = tm.homo_warping(cu(g["src"]), cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"]))
+    assert tuple(out.shape) == g["out"].shape
+    assert_costvol_close(out.cpu().numpy(), g["out"], name)
+    assert np.array_equal(out.cpu().numpy() == 0, g["out"] == 0)       # zero padding / z<1e-6 exactly
+
+
+def test_homo_warping_channels_last_and_oracle():
+    st = synthetic.make_stage(2, batch=2, n_views=3, height=64, width=96, seed=9)
+    src = st.features[1]
+    rt = geometry.stage_rot_trans(st.proj_matrix)[0]
+    want = oracle.homo_warp(src, rt, st.depth_values)
+    packed = ops.pack_sources([cu(src).contiguous(memory_format=torch.channels_last)])
+    got = ops.homo_warp_packed(packed[0], rt, cu(st.depth_values), src.shape[1])
+    assert_costvol_close(got.cpu().numpy(), want, "channels_last")
+
+
+# ----------------------------------------------------------------------------- fused cost volume
+@pytest.mark.parametrize("name", DEPTHNET_GIVEN)
+def test_cost_volume_golden(name):
+    g = golden(name)
+    feats = [cu(f) for f in g["features"]]
+    agg, views = tm.cost_volume(feats[0], feats[1:], g["rot_trans"], cu(g["depth_values"]), cu(g["view_weights"]),
+                                want_views=True)
+    assert_costvol_close(agg.cpu().numpy(), g["similarity"][:, 0], name)
+    o_views, o_agg = oracle.costvol_fwd(g["features"][0], g["features"][1:], g["rot_trans"], g["depth_values"],
+                                        g["view_weights"])
+    assert_costvol_close(views.cpu().numpy(), o_views, name + " per-view vs oracle")
+    assert_costvol_close(agg.cpu().numpy(), o_agg, name + " agg vs oracle")
+    # the two-kernel stage-1 form gives the same aggregate
+    agg2 = tm.aggregate(views, cu(g["view_weights"]))
+    assert_costvol_close(agg2.cpu().numpy(), g["similarity"][:, 0], name + " two-step")
+    # agg-only launch (the stage-2/3 hot configuration) is the same kernel family
+    agg3, none = tm.cost_volume(feats[0], feats[1:], g["rot_trans"], cu(g["depth_values"]), cu(g["view_weights"]))
+    assert none is None and torch.equal(agg3, agg)
+
+
+def test_cost_volume_plane_hypotheses_and_batch_split():
+    """[B,D] hypotheses (module.py:288) and a batch large enough to split across launches."""
+    b, n = 9, 9            # 8 source views * 9 items > 64 parameter slots -> two launches
+    st = synthetic.make_stage(1, batch=b, n_views=n, height=32, width=48, channels=8, num_depth=11, seed=4)
+    planes = st.depth_values[:, :, 0, 0].contiguous()
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    srcs = torch.stack(st.features[1:], 0)
+    o_views, o_agg = oracle.costvol_fwd(st.features[0], srcs, rt, planes, st.view_weights)
+    agg, views = tm.cost_volume(cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(planes),
+                                cu(st.view_weights), want_views=True)
+    assert_costvol_close(views.cpu().numpy(), o_views, "planes per-view")
+    assert_costvol_close(agg.cpu().numpy(), o_agg, "planes agg")
+
+
+def test_cost_volume_stage_shapes_vs_oracle():
+    """The three (C, D) kernel shapes of the cascade at a size the oracle finishes in seconds."""
+    for stage in (1, 2, 3):
+        st = synthetic.make_stage(stage, batch=1, n_views=5, height=160, width=224, seed=2)
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values,
+                                      st.view_weights, want_views=False)
+        agg, _ = tm.cost_volume(cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(st.depth_values),
+                                cu(st.view_weights))
+        assert_costvol_close(agg.cpu().numpy(), o_agg, f"stage {stage}")
+
+
+def test_cost_volume_linearity_full_size():
+    """Size-independent property at the BASELINE config-2 stage-3 size: the volume is linear in the source
+    features and in the reference features (checked without a CPU oracle)."""
+    st = synthetic.make_stage(3, batch=1, n_views=3, height=1152, width=1600, seed=1)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    ref, srcs = cu(st.features[0]), [cu(f) for f in st.features[1:]]
+    dv, vw = cu(st.depth_values), cu(st.view_weights)
+    a, _ = tm.cost_volume(ref, srcs, rt, dv, vw)
+    b2, _ = tm.cost_volume(ref, [2.0 * s for s in srcs], rt, dv, vw)
+    assert torch.equal(b2, 2.0 * a)                                         # scaling by 2 is exact in fp32
+    other = [torch.randn_like(s) for s in srcs]
+    c, _ = tm.cost_volume(ref, other, rt, dv, vw)
+    s, _ = tm.cost_volume(ref, [x + y for x, y in zip(srcs, other)], rt, dv, vw)
+    e_max, e_l2 = rel_err((a + c).cpu().numpy(), s.cpu().numpy())
+    assert e_max <= COSTVOL_REL and e_l2 <= COSTVOL_REL
+    z, _ = tm.cost_volume(torch.zeros_like(ref), srcs, rt, dv, vw)
+    assert not bool(z.any())
+
+
+def test_identity_cameras_full_size_stage1():
+    """src_proj == ref_proj at the config-2 stage-1 size: similarity_i = mean_c(ref*src) at every depth."""
+    st = synthetic.make_stage(1, batch=1, n_views=2, height=1152, width=1600, seed=3)
+    pm = st.proj_matrix.clone()
+    pm[:, 1] = pm[:, 0]
+    rt = geometry.stage_rot_trans(pm)
+    ref, src = cu(st.features[0]), cu(st.features[1])
+    _, views = tm.cost_volume(ref, [src], rt, cu(st.depth_values), None, want_views=True)
+    want = (ref * src).mean(1)                                             # [B,H,W]
+    got = views[0]
+    for d in (0, 17, 47):
+        e_max, e_l2 = rel_err(got[:, d].cpu().numpy(), want.cpu().numpy())
+        assert e_max <= COSTVOL_REL and e_l2 <= COSTVOL_REL, (d, e_max, e_l2)
+
+
+# ----------------------------------------------------------------------------- read-out
+@pytest.mark.parametrize("name", DEPTHNET_GIVEN)
+def test_softmax_wta_golden(name):
+    g = golden(name)
+    logits = cu(g["similarity"][:, 0] * g["gain"])
+    prob, idx, dep, conf = tm.softmax_wta(logits, cu(g["depth_values"]))
+    assert np.abs(prob.cpu().numpy() - g["prob_volume"]).max() <= PROB_ABS
+    assert np.abs(conf.cpu().numpy() - g["photo_confidence"]).max() <= PROB_ABS
+    rng = float(g["depth_values"].max() - g["depth_values"].min())
+    idx_c, gi = idx.cpu().numpy(), g["index"]
+    mism = idx_c != gi
+    if mism.any():
+        # allowed only where the reference's two candidates are within a few ulp
+        pv = g["prob_volume"]
+        b, y, x = np.nonzero(mism)
+        assert np.all(np.abs(pv[b, idx_c[b, y, x], y, x] - pv[b, gi[b, y, x], y, x]) <= PROB_ABS)
+    assert mism.mean() <= 1e-4
+    assert np.abs(dep.cpu().numpy() - g["depth"])[~mism].max() <= DEPTH_FRAC * rng
+    # not materialising prob gives the same maps
+    none, idx2, dep2, conf2 = tm.softmax_wta(logits, cu(g["depth_values"]), want_prob=False)
+    assert none is None and torch.equal(idx2, idx) and torch.equal(dep2, dep) and torch.equal(conf2, conf)
+
+
+@pytest.mark.parametrize("name", DEPTHNET_GIVEN + ["wta_ties"])
+def test_depth_wta_bit_exact(name):
+    g = golden(name)
+    p = g["prob_volume"] if "prob_volume" in g else g["p"]
+    idx, dep = ops.depth_wta_index(cu(p), cu(g["depth_values"]))
+    assert np.array_equal(idx.cpu().numpy(), g["index"])
+    assert np.array_equal(dep.cpu().numpy(), g["depth"])
+    assert np.array_equal(tm.depth_wta(cu(p), cu(g["depth_values"])).cpu().numpy(), g["depth"])
+
+
+def test_softmax_wta_generic_depths_vs_oracle():
+    gen = torch.Generator().manual_seed(5)
+    for d in (1, 5, 16, 33, 48, 64, 96, 192):
+        logits = 3 * torch.randn(2, d, 9, 13, generator=gen)
+        dv = 425 + 2.5 * torch.arange(d, dtype=torch.float32)[None, :, None, None] + torch.rand(2, d, 9, 13, generator=gen)
+        prob, idx, dep, conf = tm.softmax_wta(cu(logits), cu(dv))
+        o_prob, o_idx, o_dep, o_conf = oracle.softmax_wta(logits, dv)
+        assert np.abs(prob.cpu().numpy() - o_prob).max() <= PROB_ABS
+        assert np.array_equal(idx.cpu().numpy(), o_idx), d
+        assert np.array_equal(dep.cpu().numpy(), o_dep)
+        assert torch.allclose(prob.sum(1), torch.ones(2, 9, 13, device=DEV), atol=1e-5)
+
+
+def test_readout_full_size_properties():
+    """Config-2 stage-2 size: probabilities sum to 1, conf is their max, depth is a hypothesis, index agrees
+    with torch.argmax on the kernel's own probabilities (integer output: bit-exact)."""
+    st = synthetic.make_stage(2, batch=1, n_views=2, height=1152, width=1600, seed=6)
+    logits, dv = cu(st.logits), cu(st.depth_values)
+    prob, idx, dep, conf = tm.softmax_wta(logits, dv)
+    assert torch.allclose(prob.sum(1), torch.ones_like(conf), atol=1e-5)
+    assert torch.equal(conf, prob.max(1)[0])
+    assert torch.equal(idx, torch.argmax(prob, 1))
+    assert torch.equal(dep, torch.gather(dv, 1, idx[:, None]).squeeze(1))
+
+
+def test_depth_regression_fwd_bwd():
+    g = golden("regression_unpinned")
+    rng = float(g["depth_values_4d"].max() - g["depth_values_4d"].min())
+    for key_dv, key_out in (("depth_values_4d", "depth_4d"), ("depth_values_2d", "depth_2d")):
+        p = cu(g["p"]).requires_grad_(True)
+        dv = cu(g[key_dv])
+        out = tm.depth_regression(p, dv)
+        assert np.abs(out.detach().cpu().numpy() - g[key_out]).max() <= DEPTH_FRAC * rng
+        go = torch.randn_like(out)
+        out.backward(go)
+        dv4 = dv if dv.dim() == 4 else dv[:, :, None, None]
+        assert torch.allclose(p.grad, go[:, None] * dv4.expand_as(p), rtol=1e-6, atol=0)
+
+
+# ----------------------------------------------------------------------------- DepthNet drop-in
+class _Gain(torch.nn.Module):
+    def __init__(self, gain):
+        super().__init__()
+        self.gain = gain
+
+    def forward(self, x):
+        return x * self.gain
+
+
+@pytest.mark.parametrize("name", DEPTHNET_GIVEN)
+def test_depthnet_forward_given_weights(name):
+    g = golden(name)
+    net = tm.DepthNet().to(DEV).eval()
+    feats = [cu(f) for f in g["features"]]
+    with torch.no_grad():
+        out = net(feats, cu(g["proj_matrix"]), cu(g["depth_values"]), g["depth_values"].shape[1],
+                  _Gain(float(g["gain"])), view_weights=cu(g["view_weights"]))
+    assert np.abs(out["prob_volume"].cpu().numpy() - g["prob_volume"]).max() <= 5e-5   # gain 25 amplifies 1e-6 of sim
+    rng = float(g["depth_values"].max() - g["depth_values"].min())
+    idx = torch.argmax(out["prob_volume"], 1).cpu().numpy()
+    same = idx == g["index"]
+    assert same.mean() >= 0.999
+    assert np.abs(out["depth"].cpu().numpy() - g["depth"])[same].max() <= DEPTH_FRAC * rng
+    assert np.abs(out["photo_confidence"].cpu().numpy() - g["photo_confidence"]).max() <= 5e-5
+
+
+def test_depthnet_forward_learned_weights():
+    g = golden("depthnet_s1_learned")
+    net = tm.DepthNet().eval()
+    net.pixel_wise_net.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("pwn.")})
+    net = net.to(DEV)
+    feats = [cu(f) for f in g["features"]]
+    with torch.no_grad():
+        out, vw = net(feats, cu(g["proj_matrix"]), cu(g["depth_values"]), 48, _Gain(float(g["gain"])), view_weights=None)
+    assert np.abs(vw.cpu().numpy() - g["view_weights"]).max() <= 1e-5
+    assert np.abs(out["prob_volume"].cpu().numpy() - g["prob_volume"]).max() <= 5e-5
+    same = torch.argmax(out["prob_volume"], 1).cpu().numpy() == g["index"]
+    assert same.mean() >= 0.999

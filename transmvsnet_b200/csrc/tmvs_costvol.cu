@@ -1,0 +1,221 @@
+// Fused cost-volume forward for sm_100a: warp + bilinear sampling + correlation
+// (+ view-weighted aggregation) in one kernel; the B x C x D x H x W warped volume of the
+// reference (models/module.py:318-320) is never formed.
+//
+// Replaces models/TransMVSNet.py:71-93.  One thread owns one reference pixel and DC depth
+// planes; its C reference channels live in registers.  Source features are read from the
+// packed [C4][H][W][4] layout: a tap is C4 128-bit loads, and the 32 lanes of a warp (32
+// x-adjacent reference pixels) hit ~512 contiguous bytes per load, which the L1 serves in 4-5
+// wavefronts.  Neighbouring depth planes land on neighbouring source pixels, so the L1 also
+// supplies the cross-plane reuse.  The channel reduction is an in-register dot product taken
+// BEFORE the bilinear blend ("dot first": 4 dots of C, then 4 scalar weights), which is the
+// same sum as the reference's blend-then-multiply up to fp32 re-association.
+#include "tmvs_common.cuh"
+
+namespace {
+
+constexpr int kTileX = 32;
+constexpr int kTileY = 8;
+constexpr int kDC = 8;      // depth planes per thread
+
+template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG>
+__global__ void __launch_bounds__(kTileX * kTileY, 2)
+costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                   const float4 *__restrict__ packed, const float *__restrict__ depth,
+                   const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
+                   int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
+                   int n_dchunks, const __grid_constant__ TmvsGeom geom)
+{
+    const int x = blockIdx.x * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int bl = blockIdx.z / n_dchunks;            // batch item within this launch
+    const int d0 = (blockIdx.z - bl * n_dchunks) * kDC;
+    const int b = b_first + bl;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)y * W + x;
+
+    // reference channels -> registers (coalesced per channel for NCHW)
+    float4 r[C4T];
+    {
+        const float *rp = ref + b * rB + y * rH + x * rW;
+#pragma unroll
+        for (int g = 0; g < C4T; ++g) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int c = 4 * g + j;
+                v[j] = (c < C) ? __ldg(rp + c * rC) : 0.0f;
+            }
+            r[g] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    float dep[kDC];
+#pragma unroll
+    for (int k = 0; k < kDC; ++k) {
+        int d = d0 + k;
+        dep[k] = 0.0f;
+        if (d < D) dep[k] = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+    }
+    float acc[kDC];
+#pragma unroll
+    for (int k = 0; k < kDC; ++k) acc[k] = 0.0f;
+    float wsum = 1e-5f;                                // TransMVSNet.py:72
+    const float inv_c = 1.0f / (float)C;
+    const float half_w = (float)(W - 1) / 2.0f, half_h = (float)(H - 1) / 2.0f;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float xf = (float)x, yf = (float)y;
+
+    for (int i = 0; i < n_src; ++i) {
+        const float *rt = geom.rt[i * b_chunk + bl];
+        const TmvsRay ray = tmvs_ray(rt, xf, yf);
+        float wi = 0.0f;
+        if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
+        const float4 *img = packed + ((size_t)i * b_total + b) * c4 * HW;
+#pragma unroll
+        for (int k = 0; k < kDC; ++k) {
+            const int d = d0 + k;
+            if (d < D) {
+                const TmvsTaps t = tmvs_taps(ray, rt, dep[k], H, W, half_w, half_h, wm1, hm1);
+                float s = 0.0f;
+                if (t.any) {
+                    const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+                    const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+                    const float4 *p00 = img + (size_t)ya * W + xa;
+                    const float4 *p01 = img + (size_t)ya * W + xb;
+                    const float4 *p10 = img + (size_t)yb * W + xa;
+                    const float4 *p11 = img + (size_t)yb * W + xb;
+                    float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+#pragma unroll
+                    for (int g = 0; g < C4T; ++g) {
+                        if (EXACT || g < c4) {
+                            const float4 a = ldg4(p00 + g * HW);
+                            const float4 bq = ldg4(p01 + g * HW);
+                            const float4 cq = ldg4(p10 + g * HW);
+                            const float4 dq = ldg4(p11 + g * HW);
+                            s00 = dot4(r[g], a, s00);
+                            s01 = dot4(r[g], bq, s01);
+                            s10 = dot4(r[g], cq, s10);
+                            s11 = dot4(r[g], dq, s11);
+                        }
+                    }
+                    // per-tap zero padding: an out-of-bounds tap contributes nothing
+                    s = t.ok00 ? t.w00 * s00 : 0.0f;
+                    s += t.ok01 ? t.w01 * s01 : 0.0f;
+                    s += t.ok10 ? t.w10 * s10 : 0.0f;
+                    s += t.ok11 ? t.w11 * s11 : 0.0f;
+                    s *= inv_c;                               // .mean(1), TransMVSNet.py:80
+                }
+                if (VIEWS) sim_views[(((size_t)i * b_total + b) * D + d) * HW + pix] = s;
+                if (AGG) acc[k] = __fadd_rn(acc[k], __fmul_rn(s, wi));   // TransMVSNet.py:88
+            }
+        }
+        wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
+    }
+    if (AGG) {
+#pragma unroll
+        for (int k = 0; k < kDC; ++k) {
+            const int d = d0 + k;
+            if (d < D) agg[((size_t)b * D + d) * HW + pix] = __fdiv_rn(acc[k], wsum);   // :93
+        }
+    }
+}
+
+template <int C4T, bool EXACT, bool PER_PIXEL>
+int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
+                const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float4 *packed,
+                const float *depth, const float *vw, float *sim_views, float *agg, int b_total, int b_first,
+                int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsGeom &geom)
+{
+#define TMVS_LAUNCH(V, A)                                                                                 \
+    costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A><<<grid, block, 0, st>>>(                              \
+        ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,  \
+        W, n_src, n_dchunks, geom)
+    if (views && do_agg) TMVS_LAUNCH(true, true);
+    else if (views) TMVS_LAUNCH(true, false);
+    else TMVS_LAUNCH(false, true);
+#undef TMVS_LAUNCH
+    return tmvs_launch_status();
+}
+
+template <bool PER_PIXEL, typename... Args>
+int launch_c4(int c4, Args... args)
+{
+    switch (c4) {
+    case 2: return launch_mode<2, true, PER_PIXEL>(args...);
+    case 4: return launch_mode<4, true, PER_PIXEL>(args...);
+    case 8: return launch_mode<8, true, PER_PIXEL>(args...);
+    default: break;
+    }
+    if (c4 <= 4) return launch_mode<4, false, PER_PIXEL>(args...);
+    if (c4 <= 8) return launch_mode<8, false, PER_PIXEL>(args...);
+    return launch_mode<16, false, PER_PIXEL>(args...);
+}
+
+__global__ void __launch_bounds__(256)
+aggregate_fwd_kernel(const float *__restrict__ sim_views, const float *__restrict__ vw, float *__restrict__ agg,
+                     int B, int D, size_t HW, int n_src)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y, b = blockIdx.z;
+    if (p >= HW) return;
+    float s = 0.0f, wsum = 1e-5f;
+    for (int i = 0; i < n_src; ++i) {
+        const float w = __ldg(vw + ((size_t)b * n_src + i) * HW + p);
+        const float v = __ldg(sim_views + (((size_t)i * B + b) * D + d) * HW + p);
+        s = __fadd_rn(s, __fmul_rn(v, w));
+        wsum = __fadd_rn(wsum, w);
+    }
+    agg[((size_t)b * D + d) * HW + p] = __fdiv_rn(s, wsum);
+}
+
+}  // namespace
+
+extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                                const float *packed, const float *rot_trans, const float *depth, int per_pixel,
+                                const float *view_weights, float *sim_views, float *agg, int B, int C, int D,
+                                int H, int W, int n_src, tmvs_stream_t stream)
+{
+    if (!ref || !packed || !rot_trans || !depth) return TMVS_E_NULL;
+    if (!sim_views && !agg) return TMVS_E_NULL;
+    if (agg && !view_weights) return TMVS_E_NULL;
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
+    if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
+    if (((uintptr_t)packed & 15) != 0) return TMVS_E_ALIGN;
+    const int c4 = (C + 3) / 4;
+    const int n_dchunks = (D + kDC - 1) / kDC;
+    const int b_per_launch = TMVS_GEOM_SLOTS / n_src;       // rot/trans ride in the parameter bank
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 block(kTileX, kTileY);
+    for (int b0 = 0; b0 < B; b0 += b_per_launch) {
+        const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
+        TmvsGeom geom;
+        for (int i = 0; i < n_src; ++i)
+            for (int bl = 0; bl < bc; ++bl)
+                for (int k = 0; k < 12; ++k)
+                    geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
+        dim3 grid((W + kTileX - 1) / kTileX, (H + kTileY - 1) / kTileY, bc * n_dchunks);
+        int rc;
+        if (per_pixel)
+            rc = launch_c4<true>(c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,
+                                 (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D,
+                                 H, W, n_src, n_dchunks, geom);
+        else
+            rc = launch_c4<false>(c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,
+                                  (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D,
+                                  H, W, n_src, n_dchunks, geom);
+        if (rc != TMVS_OK) return rc;
+    }
+    return TMVS_OK;
+}
+
+extern "C" int tmvs_aggregate_fwd(const float *sim_views, const float *view_weights, float *agg, int B, int D,
+                                  int H, int W, int n_src, tmvs_stream_t stream)
+{
+    if (!sim_views || !view_weights || !agg) return TMVS_E_NULL;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0 || D > 65535 || B > 65535) return TMVS_E_SHAPE;
+    const size_t HW = (size_t)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), D, B);
+    aggregate_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sim_views, view_weights, agg, B, D, HW, n_src);
+    return tmvs_launch_status();
+}

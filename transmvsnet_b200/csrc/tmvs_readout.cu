@@ -1,0 +1,214 @@
+// Depth read-out kernels for sm_100a (pure streaming: HBM-bound).
+//
+// tmvs_softmax_wta_fwd fuses models/TransMVSNet.py:99-103 and models/module.py:474-482:
+// one pass over the logits gives prob = exp(log_softmax), the winner-take-all index (int64,
+// first maximal, as torch.argmax), the depth gathered at that index and the max-probability
+// confidence.  One thread per pixel; every depth plane is read/written as a coalesced 128-byte
+// row per warp, and the D logits of a pixel stay in registers between the three sweeps.
+#include "tmvs_common.cuh"
+
+namespace {
+
+// log_softmax exactly as ATen writes it: x - max - log(sum(exp(x - max)))
+template <int DT>
+__global__ void __launch_bounds__(256)
+softmax_wta_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
+                   int64_t *__restrict__ index, float *__restrict__ depth, float *__restrict__ conf, int D,
+                   size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float *x = logits + (size_t)b * D * HW + p;
+    float v[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = (d < D) ? __ldg(x + (size_t)d * HW) : 0.0f;
+    float m = v[0];
+#pragma unroll
+    for (int d = 1; d < DT; ++d)
+        if (d < D && tmvs_gt(v[d], m)) m = v[d];
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DT; ++d)
+        if (d < D) s += expf(v[d] - m);
+    const float ls = logf(s);
+    float best = 0.0f;
+    int bi = 0;
+    float *pr = prob ? prob + (size_t)b * D * HW + p : nullptr;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+        if (d < D) {
+            const float pv = expf((v[d] - m) - ls);
+            if (pr) pr[(size_t)d * HW] = pv;
+            if (d == 0 || tmvs_gt(pv, best)) { best = pv; bi = d; }
+        }
+    }
+    index[(size_t)b * HW + p] = bi;
+    depth[(size_t)b * HW + p] = __ldg(dv + ((size_t)b * D + bi) * HW + p);
+    conf[(size_t)b * HW + p] = best;
+}
+
+// Any D (<= TMVS_MAX_DEPTH): re-reads the logits for each sweep (they sit in L1/L2).
+__global__ void __launch_bounds__(256)
+softmax_wta_generic_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
+                           int64_t *__restrict__ index, float *__restrict__ depth, float *__restrict__ conf,
+                           int D, size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float *x = logits + (size_t)b * D * HW + p;
+    float m = x[0];
+    for (int d = 1; d < D; ++d) {
+        const float v = x[(size_t)d * HW];
+        if (tmvs_gt(v, m)) m = v;
+    }
+    float s = 0.0f;
+    for (int d = 0; d < D; ++d) s += expf(x[(size_t)d * HW] - m);
+    const float ls = logf(s);
+    float best = 0.0f;
+    int bi = 0;
+    float *pr = prob ? prob + (size_t)b * D * HW + p : nullptr;
+    for (int d = 0; d < D; ++d) {
+        const float pv = expf((x[(size_t)d * HW] - m) - ls);
+        if (pr) pr[(size_t)d * HW] = pv;
+        if (d == 0 || tmvs_gt(pv, best)) { best = pv; bi = d; }
+    }
+    index[(size_t)b * HW + p] = bi;
+    depth[(size_t)b * HW + p] = __ldg(dv + ((size_t)b * D + bi) * HW + p);
+    conf[(size_t)b * HW + p] = best;
+}
+
+__global__ void __launch_bounds__(256)
+depth_wta_kernel(const float *__restrict__ pvol, const float *__restrict__ dv, int64_t *__restrict__ index,
+                 float *__restrict__ depth, int D, size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float *x = pvol + (size_t)b * D * HW + p;
+    float best = __ldg(x);
+    int bi = 0;
+#pragma unroll 8
+    for (int d = 1; d < D; ++d) {
+        const float v = __ldg(x + (size_t)d * HW);
+        if (tmvs_gt(v, best)) { best = v; bi = d; }
+    }
+    if (index) index[(size_t)b * HW + p] = bi;
+    depth[(size_t)b * HW + p] = __ldg(dv + ((size_t)b * D + bi) * HW + p);
+}
+
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(256)
+depth_regression_fwd_kernel(const float *__restrict__ pvol, const float *__restrict__ dv, float *__restrict__ depth,
+                            int D, size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float *x = pvol + (size_t)b * D * HW + p;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+        const float z = PER_PIXEL ? __ldg(dv + ((size_t)b * D + d) * HW + p) : __ldg(dv + (size_t)b * D + d);
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(x + (size_t)d * HW), z));
+    }
+    depth[(size_t)b * HW + p] = acc;
+}
+
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(256)
+depth_regression_bwd_kernel(const float *__restrict__ gdepth, const float *__restrict__ dv, float *__restrict__ gp,
+                            int D, size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = blockIdx.y;
+    const float g = __ldg(gdepth + (size_t)b * HW + p);
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+        const float z = PER_PIXEL ? __ldg(dv + ((size_t)b * D + d) * HW + p) : __ldg(dv + (size_t)b * D + d);
+        gp[((size_t)b * D + d) * HW + p] = g * z;
+    }
+}
+
+inline bool bad_dims(int B, int D, int H, int W)
+{
+    return B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535 || D > TMVS_MAX_DEPTH;
+}
+
+}  // namespace
+
+extern "C" int tmvs_softmax_wta_fwd(const float *logits, const float *depth_values, float *prob, int64_t *index,
+                                    float *depth, float *conf, int B, int D, int H, int W, tmvs_stream_t stream)
+{
+    if (!logits || !depth_values || !index || !depth || !conf) return TMVS_E_NULL;
+    if (bad_dims(B, D, H, W)) return TMVS_E_SHAPE;
+    const size_t HW = (size_t)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TMVS_RO(DT) softmax_wta_kernel<DT><<<grid, 256, 0, st>>>(logits, depth_values, prob, index, depth, conf, D, HW)
+    if (D <= 8) TMVS_RO(8);
+    else if (D <= 16) TMVS_RO(16);
+    else if (D <= 32) TMVS_RO(32);
+    else if (D <= 48) TMVS_RO(48);
+    else if (D <= 64) TMVS_RO(64);
+    else softmax_wta_generic_kernel<<<grid, 256, 0, st>>>(logits, depth_values, prob, index, depth, conf, D, HW);
+#undef TMVS_RO
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_depth_wta(const float *p, const float *depth_values, int64_t *index, float *depth, int B, int D,
+                              int H, int W, tmvs_stream_t stream)
+{
+    if (!p || !depth_values || !depth) return TMVS_E_NULL;
+    if (bad_dims(B, D, H, W)) return TMVS_E_SHAPE;
+    const size_t HW = (size_t)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), B);
+    depth_wta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, depth_values, index, depth, D, HW);
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_depth_regression_fwd(const float *p, const float *depth_values, int per_pixel, float *depth,
+                                         int B, int D, int H, int W, tmvs_stream_t stream)
+{
+    if (!p || !depth_values || !depth) return TMVS_E_NULL;
+    if (bad_dims(B, D, H, W)) return TMVS_E_SHAPE;
+    const size_t HW = (size_t)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), B);
+    if (per_pixel)
+        depth_regression_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, depth_values, depth, D, HW);
+    else
+        depth_regression_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, depth_values, depth, D, HW);
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_depth_regression_bwd(const float *grad_depth, const float *depth_values, int per_pixel,
+                                         float *grad_p, int B, int D, int H, int W, tmvs_stream_t stream)
+{
+    if (!grad_depth || !depth_values || !grad_p) return TMVS_E_NULL;
+    if (bad_dims(B, D, H, W)) return TMVS_E_SHAPE;
+    const size_t HW = (size_t)H * W;
+    dim3 grid((unsigned)((HW + 255) / 256), B);
+    if (per_pixel)
+        depth_regression_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
+    else
+        depth_regression_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_version(void) { return TMVS_VERSION; }
+
+extern "C" const char *tmvs_error_string(int code)
+{
+    switch (code) {
+    case TMVS_OK: return "ok";
+    case TMVS_E_NULL: return "tmvs: required pointer is NULL";
+    case TMVS_E_SHAPE: return "tmvs: dimension out of range";
+    case TMVS_E_ALIGN: return "tmvs: pointer not 16-byte aligned";
+    case TMVS_E_UNSUPPORTED: return "tmvs: unsupported combination";
+    default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "tmvs: unknown error";
+}

@@ -37,10 +37,13 @@ def relative_rot_trans(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> torch.
 def stage_rot_trans(proj_matrix: torch.Tensor) -> torch.Tensor:
     """proj_matrix [B,N,2,4,4] -> [Nsrc,B,12] for every source view against view 0.
 
-    The 4x4 algebra runs on the CPU (the matrices come from the host dataset and are a few
-    hundred bytes); the result is passed to the kernels by value.
+    The 4x4 algebra runs with the reference's torch ops on whatever device proj_matrix lives on
+    (CPU when it comes straight from the dataset: no sync); the result goes to the host because
+    the kernels take it by value.
     """
-    pm = proj_matrix.detach().to("cpu", torch.float32)
-    views = torch.unbind(pm, 1)
-    ref = compose_projection(views[0])
-    return torch.stack([relative_rot_trans(compose_projection(v), ref) for v in views[1:]], 0)
+    with torch.no_grad():
+        pm = proj_matrix.detach().float()
+        views = torch.unbind(pm, 1)
+        ref = compose_projection(views[0])
+        rts = torch.stack([relative_rot_trans(compose_projection(v), ref) for v in views[1:]], 0)
+    return rts.cpu()
