@@ -122,6 +122,82 @@ def test_identity_cameras_full_size_stage1():
         assert e_max <= COSTVOL_REL and e_l2 <= COSTVOL_REL, (d, e_max, e_l2)
 
 
+# ----------------------------------------------------------------------------- backward (atomic-free)
+@pytest.mark.parametrize("name", DEPTHNET_GIVEN)
+def test_cost_volume_backward_golden(name):
+    """Autograd of the fused volume against the reference's autograd (grid_sample backward + mean + mul)."""
+    g = golden(name)
+    feats = [cu(f).requires_grad_(True) for f in g["features"]]
+    agg, _ = tm.cost_volume(feats[0], feats[1:], g["rot_trans"], cu(g["depth_values"]), cu(g["view_weights"]))
+    agg.backward(cu(g["grad_similarity"][:, 0]))
+    assert_costvol_close(feats[0].grad.cpu().numpy(), g["grad_features"][0], name + " grad_ref")
+    for i, f in enumerate(feats[1:]):
+        assert_costvol_close(f.grad.cpu().numpy(), g["grad_features"][1 + i], f"{name} grad_src[{i}]")
+
+
+def _backward_once(st, rt, gviews):
+    packed = ops.pack_sources([cu(f) for f in st.features[1:]])
+    return ops.costvol_backward_packed(cu(st.features[0]), packed, rt, cu(st.depth_values), gviews)
+
+
+def test_cost_volume_backward_vs_oracle_and_deterministic():
+    for stage, hw in ((1, (96, 160)), (2, (72, 104)), (3, (40, 72))):
+        st = synthetic.make_stage(stage, batch=2, n_views=3, height=hw[0], width=hw[1], seed=8)
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        n, (b, d, h, w) = len(st.features) - 1, st.depth_values.shape
+        gv = torch.randn(n, b, d, h, w, generator=torch.Generator().manual_seed(3))
+        o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, gv)
+        gref, gsrc = _backward_once(st, rt, cu(gv))
+        assert_costvol_close(gref.cpu().numpy(), o_ref, f"stage {stage} grad_ref")
+        assert_costvol_close(gsrc.cpu().numpy(), o_src, f"stage {stage} grad_src")
+        gref2, gsrc2 = _backward_once(st, rt, cu(gv))
+        assert torch.equal(gref, gref2) and torch.equal(gsrc, gsrc2)        # bit-reproducible: no float atomics
+
+
+def test_cost_volume_backward_minification_fallback():
+    """Source camera zoomed out 6x: many reference footprints share one source pixel (> 4 per cell), which
+    takes the exhaustive ordered path of the scatter kernel."""
+    st = synthetic.make_stage(2, batch=1, n_views=3, height=64, width=96, seed=12)
+    rt = geometry.stage_rot_trans(st.proj_matrix).clone()
+    rt[:, :, 0:6] /= 6.0            # rows 0-1 of rot
+    rt[:, :, 9:11] /= 6.0           # rows 0-1 of trans
+    n, (b, d, h, w) = 2, st.depth_values.shape
+    gv = torch.randn(n, b, d, h, w, generator=torch.Generator().manual_seed(4))
+    o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, gv)
+    gref, gsrc = _backward_once(st, rt, cu(gv))
+    assert_costvol_close(gref.cpu().numpy(), o_ref, "minified grad_ref")
+    assert_costvol_close(gsrc.cpu().numpy(), o_src, "minified grad_src")
+    _, gsrc2 = _backward_once(st, rt, cu(gv))
+    assert torch.equal(gsrc, gsrc2)
+
+
+def test_backward_adjoint_identity_full_size():
+    """Size-independent property at the BlendedMVS training size (config 4, one stage-2 item):
+    <G, J(src)> == <J^T(G), src> for the linear map src -> per-view similarity."""
+    st = synthetic.make_stage(2, batch=1, n_views=3, height=576, width=768, kind="unit", seed=5)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    ref, srcs, dv = cu(st.features[0]), [cu(f) for f in st.features[1:]], cu(st.depth_values)
+    packed = ops.pack_sources(srcs)
+    _, views = ops.cost_volume_packed(ref, packed, rt, dv, None, True, False)
+    gv = torch.randn_like(views)
+    _, gsrc = ops.costvol_backward_packed(ref, packed, rt, dv, gv, need_ref=False)
+    lhs = float((gv.double() * views.double()).sum())
+    rhs = float((gsrc.double() * torch.stack(srcs, 0).double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
+def test_stage1_training_graph_learned_weights():
+    """Stage 1 with PixelwiseNet in the graph: gradients reach ref, src and the PixelwiseNet parameters."""
+    g = golden("depthnet_s1_learned")
+    net = tm.DepthNet().to(DEV).train()
+    feats = [cu(f).requires_grad_(True) for f in g["features"]]
+    out, vw = net(feats, cu(g["proj_matrix"]), cu(g["depth_values"]), 48, _Gain(5.0), view_weights=None)
+    out["prob_volume"].square().sum().backward()
+    assert all(f.grad is not None and bool(torch.isfinite(f.grad).all()) and float(f.grad.abs().sum()) > 0 for f in feats)
+    assert float(net.pixel_wise_net.conv0.conv.weight.grad.abs().sum()) > 0
+    assert not vw.requires_grad
+
+
 # ----------------------------------------------------------------------------- read-out
 @pytest.mark.parametrize("name", DEPTHNET_GIVEN)
 def test_softmax_wta_golden(name):

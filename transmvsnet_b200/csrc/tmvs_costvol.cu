@@ -18,22 +18,31 @@ constexpr int kTileX = 32;
 constexpr int kTileY = 8;
 constexpr int kDC = 8;      // depth planes per thread
 
+// registers -> resident CTAs per SM: the C=32 kernel needs ~128 registers (2 CTAs), the smaller ones fit 3-4
+template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? 2 : (C4T >= 4 ? 3 : 4); };
+
 template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG>
-__global__ void __launch_bounds__(kTileX * kTileY, 2)
+__global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value)
 costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
                    const float4 *__restrict__ packed, const float *__restrict__ depth,
                    const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
                    int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
                    int n_dchunks, const __grid_constant__ TmvsGeom geom)
 {
-    const int x = blockIdx.x * kTileX + threadIdx.x;
+    // the depth chunk is the FASTEST block index: the CTAs that sweep the same source neighbourhood for
+    // different depth planes are co-scheduled, so each source line comes from HBM once and from L2 after
+    __shared__ float acc_s[AGG ? kDC : 1][kTileX * kTileY];
+    const int chunk = blockIdx.x % n_dchunks;
+    const int x = (blockIdx.x / n_dchunks) * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
     if (x >= W || y >= H) return;
-    const int bl = blockIdx.z / n_dchunks;            // batch item within this launch
-    const int d0 = (blockIdx.z - bl * n_dchunks) * kDC;
+    const int tid = threadIdx.y * kTileX + threadIdx.x;
+    const int bl = blockIdx.z;                        // batch item within this launch
+    const int d0 = chunk * kDC;
+    const int nd = min(kDC, D - d0);
     const int b = b_first + bl;
-    const size_t HW = (size_t)H * W;
-    const size_t pix = (size_t)y * W + x;
+    const int HW = H * W;
+    const int pix = y * W + x;
 
     // reference channels -> registers (coalesced per channel for NCHW)
     float4 r[C4T];
@@ -50,20 +59,15 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
             r[g] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    float dep[kDC];
+    const float *dep_p = PER_PIXEL ? depth + ((size_t)b * D + d0) * HW + pix : depth + (size_t)b * D + d0;
+    const int dep_stride = PER_PIXEL ? HW : 1;
+    if (AGG) {
 #pragma unroll
-    for (int k = 0; k < kDC; ++k) {
-        int d = d0 + k;
-        dep[k] = 0.0f;
-        if (d < D) dep[k] = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+        for (int k = 0; k < kDC; ++k) acc_s[k][tid] = 0.0f;
     }
-    float acc[kDC];
-#pragma unroll
-    for (int k = 0; k < kDC; ++k) acc[k] = 0.0f;
     float wsum = 1e-5f;                                // TransMVSNet.py:72
     const float inv_c = 1.0f / (float)C;
-    const float half_w = (float)(W - 1) / 2.0f, half_h = (float)(H - 1) / 2.0f;
-    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const TmvsDims dims = tmvs_dims(H, W);
     const float xf = (float)x, yf = (float)y;
 
     for (int i = 0; i < n_src; ++i) {
@@ -72,52 +76,47 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
         float wi = 0.0f;
         if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
         const float4 *img = packed + ((size_t)i * b_total + b) * c4 * HW;
+        float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
+#pragma unroll 2
+        for (int k = 0; k < nd; ++k) {
+            const TmvsTaps t = tmvs_taps(ray, rt, __ldg(dep_p + (size_t)k * dep_stride), dims);
+            float s = 0.0f;
+            if (t.any) {
+                const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+                const int ya = min(max(t.y0, 0), H - 1) * W, yb = min(max(t.y0 + 1, 0), H - 1) * W;
+                const float4 *p00 = img + (ya + xa);
+                const float4 *p01 = img + (ya + xb);
+                const float4 *p10 = img + (yb + xa);
+                const float4 *p11 = img + (yb + xb);
+                float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < kDC; ++k) {
-            const int d = d0 + k;
-            if (d < D) {
-                const TmvsTaps t = tmvs_taps(ray, rt, dep[k], H, W, half_w, half_h, wm1, hm1);
-                float s = 0.0f;
-                if (t.any) {
-                    const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-                    const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-                    const float4 *p00 = img + (size_t)ya * W + xa;
-                    const float4 *p01 = img + (size_t)ya * W + xb;
-                    const float4 *p10 = img + (size_t)yb * W + xa;
-                    const float4 *p11 = img + (size_t)yb * W + xb;
-                    float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
-#pragma unroll
-                    for (int g = 0; g < C4T; ++g) {
-                        if (EXACT || g < c4) {
-                            const float4 a = ldg4(p00 + g * HW);
-                            const float4 bq = ldg4(p01 + g * HW);
-                            const float4 cq = ldg4(p10 + g * HW);
-                            const float4 dq = ldg4(p11 + g * HW);
-                            s00 = dot4(r[g], a, s00);
-                            s01 = dot4(r[g], bq, s01);
-                            s10 = dot4(r[g], cq, s10);
-                            s11 = dot4(r[g], dq, s11);
-                        }
+                for (int g = 0; g < C4T; ++g) {
+                    if (EXACT || g < c4) {
+                        const float4 a = ldg4(p00 + (size_t)g * HW);
+                        const float4 bq = ldg4(p01 + (size_t)g * HW);
+                        const float4 cq = ldg4(p10 + (size_t)g * HW);
+                        const float4 dq = ldg4(p11 + (size_t)g * HW);
+                        s00 = dot4(r[g], a, s00);
+                        s01 = dot4(r[g], bq, s01);
+                        s10 = dot4(r[g], cq, s10);
+                        s11 = dot4(r[g], dq, s11);
                     }
-                    // per-tap zero padding: an out-of-bounds tap contributes nothing
-                    s = t.ok00 ? t.w00 * s00 : 0.0f;
-                    s += t.ok01 ? t.w01 * s01 : 0.0f;
-                    s += t.ok10 ? t.w10 * s10 : 0.0f;
-                    s += t.ok11 ? t.w11 * s11 : 0.0f;
-                    s *= inv_c;                               // .mean(1), TransMVSNet.py:80
                 }
-                if (VIEWS) sim_views[(((size_t)i * b_total + b) * D + d) * HW + pix] = s;
-                if (AGG) acc[k] = __fadd_rn(acc[k], __fmul_rn(s, wi));   // TransMVSNet.py:88
+                // per-tap zero padding: an out-of-bounds tap contributes nothing
+                s = t.ok00 ? t.w00 * s00 : 0.0f;
+                s += t.ok01 ? t.w01 * s01 : 0.0f;
+                s += t.ok10 ? t.w10 * s10 : 0.0f;
+                s += t.ok11 ? t.w11 * s11 : 0.0f;
+                s *= inv_c;                               // .mean(1), TransMVSNet.py:80
             }
+            if (VIEWS) __stcs(out_v + (size_t)k * HW, s);
+            if (AGG) acc_s[k][tid] = __fadd_rn(acc_s[k][tid], __fmul_rn(s, wi));   // TransMVSNet.py:88
         }
         wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
     }
     if (AGG) {
-#pragma unroll
-        for (int k = 0; k < kDC; ++k) {
-            const int d = d0 + k;
-            if (d < D) agg[((size_t)b * D + d) * HW + pix] = __fdiv_rn(acc[k], wsum);   // :93
-        }
+        float *out_a = agg + ((size_t)b * D + d0) * HW + pix;
+        for (int k = 0; k < nd; ++k) __stcs(out_a + (size_t)k * HW, __fdiv_rn(acc_s[k][tid], wsum));   // :93
     }
 }
 
@@ -181,6 +180,7 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
     if (agg && !view_weights) return TMVS_E_NULL;
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
     if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
+    if ((size_t)H * W * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;   // 32-bit offsets inside one view
     if (((uintptr_t)packed & 15) != 0) return TMVS_E_ALIGN;
     const int c4 = (C + 3) / 4;
     const int n_dchunks = (D + kDC - 1) / kDC;
@@ -194,7 +194,7 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
             for (int bl = 0; bl < bc; ++bl)
                 for (int k = 0; k < 12; ++k)
                     geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
-        dim3 grid((W + kTileX - 1) / kTileX, (H + kTileY - 1) / kTileY, bc * n_dchunks);
+        dim3 grid(((W + kTileX - 1) / kTileX) * n_dchunks, (H + kTileY - 1) / kTileY, bc);
         int rc;
         if (per_pixel)
             rc = launch_c4<true>(c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,

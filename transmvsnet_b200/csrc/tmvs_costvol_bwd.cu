@@ -1,6 +1,419 @@
-// placeholder, replaced below
+// Backward of the fused cost volume wrt the features, for sm_100a -- deterministic and atomic-free.
+//
+// Autograd of models/module.py:318-320 (grid_sample) and models/TransMVSNet.py:80 ((warped*ref).mean(1)),
+// SURVEY.md 3.4.  Input: G_i = dL/d similarity_i  [Nsrc][B][D][H][W].
+//
+//   grad_ref[b,c,p]   = 1/C * sum_i sum_d G_i[d,p] * warped_i[c,d,p]               -- a gather
+//   grad_src_i[b,c,q] = 1/C * sum_{(p,d,tap) -> q} G_i[d,p] * w_tap(p,d) * ref[c,p] -- the grid_sample scatter
+//
+// ATen does the scatter with float atomicAdd (cuda/GridSampler.cuh:250-260), so its result depends on the
+// order the atomics retire.  Here the scatter is turned into a gather with an explicit order:
+//   1. bwd_bbox_kernel: for every (view, reference tile T of 32x8 pixels, depth plane d) the bounding box of
+//      the source pixels T's bilinear footprints touch -- exact, from the same coordinate code as the forward.
+//   2. bwd_src_kernel: one CTA OWNS one 32x8 tile S of grad_src (one thread per source pixel, its C
+//      accumulators in registers).  It scans the boxes, and for every (T, d) that overlaps S, in (T, d)
+//      order:  phase 1 -- thread t recomputes the footprint of reference pixel t of T and registers itself in
+//      a shared-memory cell grid indexed by its north-west source pixel (a few rounds of plain stores; which
+//      thread wins a round is irrelevant because phase 2 orders the ids);  phase 2 -- each owner reads the <= 4 cells whose taps
+//      hit its pixel, SORTS the registered thread ids, and accumulates k * ref[:, p] in that order.
+//   Every output element is written exactly once by its owner, in a fixed summation order: no atomics on
+//   data, bit-reproducible run to run.
+// grad_ref is a plain gather (forward-shaped kernel), split over views and reduced in view order.
 #include "tmvs_common.cuh"
-extern "C" size_t tmvs_costvol_bwd_workspace_bytes(int, int, int, int, int, int) { return 0; }
-extern "C" int tmvs_costvol_bwd(const float *, int64_t, int64_t, int64_t, int64_t, const float *, const float *,
-                                const float *, int, const float *, float *, float *, void *, size_t, int, int, int,
-                                int, int, int, tmvs_stream_t) { return TMVS_E_UNSUPPORTED; }
+
+extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
+                                 float *packed, int B, int C, int H, int W, tmvs_stream_t stream);
+
+namespace {
+
+constexpr int kTX = 32, kTY = 8, kThreads = kTX * kTY;
+constexpr int kCellW = kTX + 1, kCellH = kTY + 1, kCells = kCellW * kCellH;
+constexpr int kSlots = 4;          // footprints sharing one north-west pixel handled by the fast path
+constexpr int kEmpty = 0x7fffffff;
+
+// --------------------------------------------------------------------------------------------- grad_ref
+template <int C4T, bool EXACT, bool PER_PIXEL>
+__global__ void __launch_bounds__(kThreads, 2)
+bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ depth, const float *__restrict__ G,
+               float *__restrict__ partial, int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W,
+               const __grid_constant__ TmvsGeom geom)
+{
+    const int x = blockIdx.x * kTX + threadIdx.x;
+    const int y = blockIdx.y * kTY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
+    const int b = b_first + bl;
+    const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
+    const float *rt = geom.rt[i * b_chunk + bl];
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const float inv_c = 1.0f / (float)C;
+    const TmvsDims dims = tmvs_dims(H, W);
+    const float4 *img = packed + ((size_t)i * b_total + b) * c4 * HW;
+    const float *gp = G + ((size_t)i * b_total + b) * D * HW + pix;
+    float4 acc[C4T];
+#pragma unroll
+    for (int g = 0; g < C4T; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < D; ++d) {
+        const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+        const float gw = __ldg(gp + (size_t)d * HW) * inv_c;
+        const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
+        if (!t.any) continue;
+        const float k00 = t.ok00 ? gw * t.w00 : 0.0f, k01 = t.ok01 ? gw * t.w01 : 0.0f;
+        const float k10 = t.ok10 ? gw * t.w10 : 0.0f, k11 = t.ok11 ? gw * t.w11 : 0.0f;
+        const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+        const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+        const float4 *p00 = img + (size_t)ya * W + xa, *p01 = img + (size_t)ya * W + xb;
+        const float4 *p10 = img + (size_t)yb * W + xa, *p11 = img + (size_t)yb * W + xb;
+#pragma unroll
+        for (int g = 0; g < C4T; ++g) {
+            if (EXACT || g < c4) {
+                const float4 a = ldg4(p00 + g * HW), bq = ldg4(p01 + g * HW);
+                const float4 cq = ldg4(p10 + g * HW), dq = ldg4(p11 + g * HW);
+                acc[g].x += k00 * a.x + k01 * bq.x + k10 * cq.x + k11 * dq.x;
+                acc[g].y += k00 * a.y + k01 * bq.y + k10 * cq.y + k11 * dq.y;
+                acc[g].z += k00 * a.z + k01 * bq.z + k10 * cq.z + k11 * dq.z;
+                acc[g].w += k00 * a.w + k01 * bq.w + k10 * cq.w + k11 * dq.w;
+            }
+        }
+    }
+    float *o = partial + (((size_t)i * b_total + b) * C) * HW + pix;
+#pragma unroll
+    for (int g = 0; g < C4T; ++g) {
+        const float v[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * g + j < C) o[(size_t)(4 * g + j) * HW] = v[j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bwd_ref_reduce_kernel(const float *__restrict__ partial, float *__restrict__ grad_ref, size_t n, int n_src)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float s = __ldg(partial + k);
+    for (int i = 1; i < n_src; ++i) s += __ldg(partial + (size_t)i * n + k);     // fixed view order
+    grad_ref[k] = s;
+}
+
+// --------------------------------------------------------------------------------------------- grad_src
+// Bounding box (inclusive, in source pixels, in-bounds taps only) of the footprints of tile T at plane d.
+template <bool PER_PIXEL>
+__global__ void __launch_bounds__(kThreads)
+bwd_bbox_kernel(const float *__restrict__ depth, int4 *__restrict__ bbox, int b_first, int b_chunk, int D, int H,
+                int W, int n_tx, int n_tiles, const __grid_constant__ TmvsGeom geom)
+{
+    __shared__ int red[4][kTY];
+    const int x = blockIdx.x * kTX + threadIdx.x;
+    const int y = blockIdx.y * kTY + threadIdx.y;
+    const bool valid = x < W && y < H;
+    const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
+    const int b = b_first + bl;
+    const size_t HW = (size_t)H * W, pix = (size_t)min(y, H - 1) * W + min(x, W - 1);
+    const float *rt = geom.rt[i * b_chunk + bl];
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const TmvsDims dims = tmvs_dims(H, W);
+    const int tile = blockIdx.y * n_tx + blockIdx.x;
+    int4 *out = bbox + ((size_t)blockIdx.z * n_tiles + tile) * D;
+    const int warp = threadIdx.y, lane = threadIdx.x;
+    for (int d = 0; d < D; ++d) {
+        const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+        const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
+        int lo_x = kEmpty, lo_y = kEmpty, hi_x = -1, hi_y = -1;
+        if (valid && t.any) {
+            lo_x = max(t.x0, 0); hi_x = min(t.x0 + 1, W - 1);
+            lo_y = max(t.y0, 0); hi_y = min(t.y0 + 1, H - 1);
+        }
+        lo_x = __reduce_min_sync(0xffffffffu, lo_x);
+        lo_y = __reduce_min_sync(0xffffffffu, lo_y);
+        hi_x = __reduce_max_sync(0xffffffffu, hi_x);
+        hi_y = __reduce_max_sync(0xffffffffu, hi_y);
+        if (lane == 0) { red[0][warp] = lo_x; red[1][warp] = lo_y; red[2][warp] = hi_x; red[3][warp] = hi_y; }
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            int4 r = make_int4(kEmpty, kEmpty, -1, -1);
+#pragma unroll
+            for (int w = 0; w < kTY; ++w) {
+                r.x = min(r.x, red[0][w]); r.y = min(r.y, red[1][w]);
+                r.z = max(r.z, red[2][w]); r.w = max(r.w, red[3][w]);
+            }
+            out[d] = r;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void cswap(int &a, int &b)
+{
+    const int lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
+}
+
+template <int C4T, bool EXACT, bool PER_PIXEL>
+__global__ void __launch_bounds__(kThreads, 2)
+bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth, const float *__restrict__ G,
+               const int4 *__restrict__ bbox, float *__restrict__ grad_src, int b_total, int b_first, int b_chunk,
+               int C, int c4, int D, int H, int W, int n_tx, int n_tiles, const __grid_constant__ TmvsGeom geom)
+{
+    __shared__ int cell[kSlots][kCells];
+    __shared__ float krec[4][kThreads];
+    __shared__ int pixrec[kThreads], x0rec[kThreads], y0rec[kThreads];
+    __shared__ int hits[kThreads];
+    __shared__ int wcount[kTY];
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
+    const int s_x = blockIdx.x * kTX, s_y = blockIdx.y * kTY;      // the owned source tile
+    const int qx = s_x + tx, qy = s_y + ty;
+    const bool q_valid = qx < W && qy < H;
+    const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
+    const int b = b_first + bl;
+    const size_t HW = (size_t)H * W;
+    const float *rt = geom.rt[i * b_chunk + bl];
+    const float inv_c = 1.0f / (float)C;
+    const TmvsDims dims = tmvs_dims(H, W);
+    const float4 *rimg = refp + (size_t)b * c4 * HW;
+    const float *gview = G + ((size_t)i * b_total + b) * D * HW;
+    const int4 *boxes = bbox + (size_t)blockIdx.z * n_tiles * D;
+    const int n_pairs = n_tiles * D;
+
+    float4 acc[C4T];
+#pragma unroll
+    for (int g = 0; g < C4T; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto accumulate = [&](float k, int off) {
+#pragma unroll
+        for (int g = 0; g < C4T; ++g) {
+            if (EXACT || g < c4) {
+                const float4 rv = ldg4(rimg + g * HW + off);
+                acc[g].x = fmaf(k, rv.x, acc[g].x);
+                acc[g].y = fmaf(k, rv.y, acc[g].y);
+                acc[g].z = fmaf(k, rv.z, acc[g].z);
+                acc[g].w = fmaf(k, rv.w, acc[g].w);
+            }
+        }
+    };
+
+    for (int base = 0; base < n_pairs; base += kThreads) {
+        // ---- which (T, d) pairs of this chunk touch S?  ordered compaction -> deterministic visiting order
+        const int j = base + tid;
+        bool hit = false;
+        if (j < n_pairs) {
+            const int4 bb = __ldg(boxes + j);
+            hit = bb.x <= s_x + kTX - 1 && bb.z >= s_x && bb.y <= s_y + kTY - 1 && bb.w >= s_y;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (tx == 0) wcount[ty] = __popc(ballot);
+        __syncthreads();
+        int prefix = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kTY; ++w) {
+            const int c = wcount[w];
+            if (w < ty) prefix += c;
+            total += c;
+        }
+        if (hit) hits[prefix + __popc(ballot & ((1u << tx) - 1u))] = j;
+        __syncthreads();
+
+        for (int h = 0; h < total; ++h) {
+            const int jj = hits[h];
+            const int tile = jj / D, d = jj - tile * D;
+            const int t_y = tile / n_tx, t_x = tile - t_y * n_tx;
+            // ---- phase 1: thread t = reference pixel t of tile T at plane d
+            const int px = t_x * kTX + tx, py = t_y * kTY + ty;
+            int my_cell = -1;
+            float k00 = 0.f, k01 = 0.f, k10 = 0.f, k11 = 0.f;
+            int x0 = kEmpty, y0 = kEmpty;
+            if (px < W && py < H) {
+                const size_t pix = (size_t)py * W + px;
+                const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+                const TmvsRay ray = tmvs_ray(rt, (float)px, (float)py);
+                const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
+                const int cx = t.x0 - s_x + 1, cy = t.y0 - s_y + 1;
+                if (t.any && cx >= 0 && cx < kCellW && cy >= 0 && cy < kCellH) {
+                    const float gw = __ldg(gview + (size_t)d * HW + pix) * inv_c;
+                    k00 = t.ok00 ? gw * t.w00 : 0.0f; k01 = t.ok01 ? gw * t.w01 : 0.0f;
+                    k10 = t.ok10 ? gw * t.w10 : 0.0f; k11 = t.ok11 ? gw * t.w11 : 0.0f;
+                    my_cell = cy * kCellW + cx;
+                    x0 = t.x0; y0 = t.y0;
+                }
+            }
+            krec[0][tid] = k00; krec[1][tid] = k01; krec[2][tid] = k10; krec[3][tid] = k11;
+            pixrec[tid] = py * W + px;
+            x0rec[tid] = x0; y0rec[tid] = y0;
+            for (int c = tid; c < kSlots * kCells; c += kThreads) (&cell[0][0])[c] = kEmpty;
+            __syncthreads();
+            // registration rounds: plain stores; one registrant per cell per round survives, the rest retry.
+            // WHICH one survives does not matter: phase 2 sorts the ids of a cell before summing.
+            bool pending = my_cell >= 0;
+            int left = 0;
+#pragma unroll 1
+            for (int r = 0; r < kSlots; ++r) {
+                if (pending) cell[r][my_cell] = tid;
+                __syncthreads();
+                if (pending && cell[r][my_cell] == tid) pending = false;
+                left = __syncthreads_or(pending);
+                if (!left) break;
+            }
+            // ---- phase 2: the owner of source pixel q gathers the taps that land on it
+            if (q_valid) {
+                if (!left) {
+                    const int c00 = (ty + 1) * kCellW + (tx + 1), c01 = (ty + 1) * kCellW + tx;
+                    const int c10 = ty * kCellW + (tx + 1), c11 = ty * kCellW + tx;
+                    const int cls_cell[4] = {c00, c01, c10, c11};
+#pragma unroll
+                    for (int cls = 0; cls < 4; ++cls) {
+                        int i0 = cell[0][cls_cell[cls]], i1 = cell[1][cls_cell[cls]];
+                        int i2 = cell[2][cls_cell[cls]], i3 = cell[3][cls_cell[cls]];
+                        if (i1 != kEmpty) {           // several footprints share the cell: fix the order
+                            cswap(i0, i1); cswap(i2, i3); cswap(i0, i2); cswap(i1, i3); cswap(i1, i2);
+                        }
+                        const int ids[4] = {i0, i1, i2, i3};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (ids[u] != kEmpty) {
+                                const float k = krec[cls][ids[u]];
+                                if (k != 0.0f) accumulate(k, pixrec[ids[u]]);
+                            }
+                        }
+                    }
+                } else {
+                    // more than kSlots footprints on one cell (strong minification): exhaustive, still ordered
+#pragma unroll 1
+                    for (int cls = 0; cls < 4; ++cls) {
+                        const int want_x = qx - (cls & 1), want_y = qy - (cls >> 1);
+#pragma unroll 1
+                        for (int t2 = 0; t2 < kThreads; ++t2) {
+                            if (x0rec[t2] == want_x && y0rec[t2] == want_y) {
+                                const float k = krec[cls][t2];
+                                if (k != 0.0f) accumulate(k, pixrec[t2]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (q_valid) {
+        float *o = grad_src + (((size_t)i * b_total + b) * C) * HW + (size_t)qy * W + qx;
+#pragma unroll
+        for (int g = 0; g < C4T; ++g) {
+            const float v[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2)
+                if (4 * g + j2 < C) o[(size_t)(4 * g + j2) * HW] = v[j2];
+        }
+    }
+}
+
+inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct BwdWorkspace {
+    size_t ref_packed, partial, bbox, total;
+};
+
+inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t n_tiles = (size_t)((W + kTX - 1) / kTX) * ((H + kTY - 1) / kTY);
+    BwdWorkspace ws;
+    ws.ref_packed = 0;
+    ws.partial = align256((size_t)B * ((C + 3) / 4) * HW * 16);
+    ws.bbox = ws.partial + align256((size_t)n_src * B * C * HW * 4);
+    ws.total = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
+    return ws;
+}
+
+template <bool PER_PIXEL>
+int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st, const float4 *packed,
+               const float4 *refp, const float *depth, const float *G, float *partial, int4 *bbox, float *grad_src,
+               int b_total, int b_first, int b_chunk, int C, int D, int H, int W, int n_tx, int n_tiles,
+               const TmvsGeom &geom)
+{
+    dim3 block(kTX, kTY);
+#define TMVS_BWD(C4T, EX)                                                                                          \
+    do {                                                                                                           \
+        if (want_ref)                                                                                              \
+            bwd_ref_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(packed, depth, G, partial, b_total, b_first, \
+                                                                       b_chunk, C, c4, D, H, W, geom);             \
+        if (want_src) {                                                                                            \
+            bwd_bbox_kernel<PER_PIXEL><<<grid, block, 0, st>>>(depth, bbox, b_first, b_chunk, D, H, W, n_tx,       \
+                                                               n_tiles, geom);                                     \
+            bwd_src_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(refp, depth, G, bbox, grad_src, b_total,    \
+                                                                       b_first, b_chunk, C, c4, D, H, W, n_tx,     \
+                                                                       n_tiles, geom);                             \
+        }                                                                                                          \
+    } while (0)
+    if (c4 == 2) TMVS_BWD(2, true);
+    else if (c4 == 4) TMVS_BWD(4, true);
+    else if (c4 == 8) TMVS_BWD(8, true);
+    else if (c4 < 4) TMVS_BWD(4, false);
+    else if (c4 < 8) TMVS_BWD(8, false);
+    else TMVS_BWD(16, false);
+#undef TMVS_BWD
+    return tmvs_launch_status();
+}
+
+}  // namespace
+
+extern "C" size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src)
+{
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return 0;
+    return bwd_layout(B, C, D, H, W, n_src).total;
+}
+
+extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *packed,
+                                const float *rot_trans, const float *depth, int per_pixel, const float *grad_views,
+                                float *grad_ref, float *grad_src, void *workspace, size_t workspace_bytes, int B,
+                                int C, int D, int H, int W, int n_src, tmvs_stream_t stream)
+{
+    if (!ref || !packed || !rot_trans || !depth || !grad_views || !workspace) return TMVS_E_NULL;
+    if (!grad_ref && !grad_src) return TMVS_E_NULL;
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
+    if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
+    if ((size_t)H * W > 0x7fffffffu) return TMVS_E_SHAPE;
+    if (((uintptr_t)packed & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return TMVS_E_ALIGN;
+    const BwdWorkspace ws = bwd_layout(B, C, D, H, W, n_src);
+    if (workspace_bytes < ws.total) return TMVS_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *wsp = (char *)workspace;
+    float *refp = (float *)(wsp + ws.ref_packed);
+    float *partial = (float *)(wsp + ws.partial);
+    int4 *bbox = (int4 *)(wsp + ws.bbox);
+    const int c4 = (C + 3) / 4;
+    const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY, n_tiles = n_tx * n_ty;
+    const size_t HW = (size_t)H * W;
+    if (grad_src) {   // reference features in the packed layout: the scatter's "value" operand
+        const float *one[1] = {ref};
+        int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, stream);
+        if (rc != TMVS_OK) return rc;
+    }
+    const int b_per_launch = TMVS_GEOM_SLOTS / n_src;
+    for (int b0 = 0; b0 < B; b0 += b_per_launch) {
+        const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
+        TmvsGeom geom;
+        for (int i = 0; i < n_src; ++i)
+            for (int bl = 0; bl < bc; ++bl)
+                for (int k = 0; k < 12; ++k)
+                    geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
+        dim3 grid(n_tx, n_ty, n_src * bc);
+        // the bbox table of this launch is indexed by blockIdx.z = i * bc + bl
+        int rc;
+        if (per_pixel)
+            rc = launch_bwd<true>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
+                                  (const float4 *)refp, depth, grad_views, partial, bbox, grad_src, B, b0, bc, C, D, H,
+                                  W, n_tx, n_tiles, geom);
+        else
+            rc = launch_bwd<false>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
+                                   (const float4 *)refp, depth, grad_views, partial, bbox, grad_src, B, b0, bc, C, D, H,
+                                   W, n_tx, n_tiles, geom);
+        if (rc != TMVS_OK) return rc;
+    }
+    if (grad_ref) {
+        const size_t n = (size_t)B * C * HW;
+        bwd_ref_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, grad_ref, n, n_src);
+        int rc = tmvs_launch_status();
+        if (rc != TMVS_OK) return rc;
+    }
+    return TMVS_OK;
+}

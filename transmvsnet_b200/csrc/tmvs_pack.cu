@@ -36,6 +36,50 @@ pack_sources_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
     packed[((size_t)vb * c4 + g) * HW + p] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// NCHW fast path (x contiguous, W % 4 == 0, 16-byte aligned rows): one thread moves a 4-pixel x 4-channel
+// block -- four 128-bit loads (one per channel plane), a register transpose, four 128-bit stores.
+__global__ void __launch_bounds__(256)
+pack_sources_nchw4_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float4 *__restrict__ packed,
+                          int B, int C, int c4, int H, int W)
+{
+    const int wq = W >> 2;
+    const size_t nquads = (size_t)H * wq;
+    const size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qd >= nquads) return;
+    const int g = blockIdx.y;
+    const int vb = blockIdx.z;
+    const int view = vb / B, b = vb - view * B;
+    const int y = (int)(qd / wq), xq = (int)(qd - (size_t)y * wq);
+    const float *base = src.p[view] + b * sB + y * sH + 4 * xq;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = 4 * g + j;
+        v[j] = (c < C) ? __ldg(reinterpret_cast<const float4 *>(base + c * sC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 *o = packed + ((size_t)vb * c4 + g) * H * W + (size_t)y * W + 4 * xq;
+    o[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+    o[1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+    o[2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+    o[3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+}
+
+// channels_last fast path (channel stride 1, C % 4 == 0, aligned): a pure 128-bit permuting copy.
+__global__ void __launch_bounds__(256)
+pack_sources_nhwc_kernel(SrcPtrs src, int64_t sB, int64_t sH, int64_t sW, float4 *__restrict__ packed,
+                         int B, int c4, int H, int W)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int g = blockIdx.y;
+    const int vb = blockIdx.z;
+    const int view = vb / B, b = vb - view * B;
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    const float *base = src.p[view] + b * sB + y * sH + x * sW + 4 * g;
+    packed[((size_t)vb * c4 + g) * HW + p] = __ldg(reinterpret_cast<const float4 *>(base));
+}
+
 constexpr int kWarpDC = 4;   // depth planes per thread in the drop-in warp
 
 template <bool PER_PIXEL>
@@ -54,15 +98,14 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
     const size_t pix = (size_t)y * W + x;
     const float *rt = geom.rt[bl];
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
-    const float half_w = (float)(W - 1) / 2.0f, half_h = (float)(H - 1) / 2.0f;
-    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const TmvsDims dims = tmvs_dims(H, W);
     const float4 *img = packed + (size_t)b * c4 * HW;
 #pragma unroll
     for (int k = 0; k < kWarpDC; ++k) {
         const int d = d0 + k;
         if (d >= D) break;
         const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
-        const TmvsTaps t = tmvs_taps(ray, rt, dep, H, W, half_w, half_h, wm1, hm1);
+        const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
         float *o = out + (((size_t)b * C) * D + d) * HW + pix;
         const size_t c_stride = (size_t)D * HW;
         if (!t.any) {
@@ -120,8 +163,19 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
     }
     const int c4 = (C + 3) / 4;
     const size_t HW = (size_t)H * W;
-    dim3 grid((unsigned)((HW + 255) / 256), c4, n_src * B);
-    pack_sources_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ptrs, sB, sC, sH, sW, (float4 *)packed, B, C, c4, H, W);
+    bool aligned = true;
+    for (int i = 0; i < n_src; ++i) aligned = aligned && (((uintptr_t)src[i] & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aligned && sW == 1 && (W & 3) == 0 && (sH & 3) == 0 && (sC & 3) == 0 && (sB & 3) == 0) {
+        dim3 grid((unsigned)((HW / 4 + 255) / 256), c4, n_src * B);
+        pack_sources_nchw4_kernel<<<grid, 256, 0, st>>>(ptrs, sB, sC, sH, (float4 *)packed, B, C, c4, H, W);
+    } else if (aligned && sC == 1 && (C & 3) == 0 && (sW & 3) == 0 && (sH & 3) == 0 && (sB & 3) == 0) {
+        dim3 grid((unsigned)((HW + 255) / 256), c4, n_src * B);
+        pack_sources_nhwc_kernel<<<grid, 256, 0, st>>>(ptrs, sB, sH, sW, (float4 *)packed, B, c4, H, W);
+    } else {
+        dim3 grid((unsigned)((HW + 255) / 256), c4, n_src * B);
+        pack_sources_kernel<<<grid, 256, 0, st>>>(ptrs, sB, sC, sH, sW, (float4 *)packed, B, C, c4, H, W);
+    }
     return tmvs_launch_status();
 }
 
