@@ -16,9 +16,9 @@
  *   - tensors are contiguous in the layouts written beside them; feature inputs additionally
  *     take element strides so NCHW and torch.channels_last tensors are both accepted;
  *   - "packed" source features use the kernel-native blocked channel-last layout
- *       [Nsrc][B][C4][H][W][4],  C4 = ceil(C/4), zero padded,
- *     produced by tmvs_pack_sources(): one bilinear tap of 4 channels is one 128-bit load and
- *     x-adjacent pixels are adjacent in memory;
+ *       [Nsrc][B][H][Wb][C4][8 px][4 ch],  C4 = ceil(C/4) (zero padded), Wb = ceil(W/8),
+ *     produced by tmvs_pack_sources(): one bilinear tap of 4 channels is one 128-bit load, 8
+ *     x-adjacent pixels share a 128-byte line and the C4 groups of a pixel are 128 bytes apart;
  *   - rot_trans is a HOST array [Nsrc][B][12]: 3x3 `rot` (row major) then `trans` of
  *       proj = src_proj @ inverse(ref_proj)            (models/module.py:295-297),
  *     computed by the caller with the same torch ops as the reference;
@@ -55,7 +55,7 @@ const char *tmvs_error_string(int code);
 size_t tmvs_packed_bytes(int n_src, int B, int C, int H, int W);
 
 /*
- * Layout pre-pass: the N source feature maps  ->  packed [Nsrc][B][C4][H][W][4].
+ * Layout pre-pass: the N source feature maps  ->  packed [Nsrc][B][H][Wb][C4][8][4].
  * src[i] points at view i's [B,C,H,W] tensor with element strides (sB,sC,sH,sW), so the
  * NCHW output of the reference's FeatureNet/FMT (models/module.py:399-422, models/FMT.py:212-230)
  * and channels_last tensors are both read in place.   src is a HOST array of device pointers.
@@ -65,7 +65,7 @@ int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC
 
 /*
  * Drop-in homo_warping (models/module.py:284-322) for ONE source view: materialises the
- * warped volume out[B][C][D][H][W].  packed_view = this view's slice [B][C4][H][W][4];
+ * warped volume out[B][C][D][H][W].  packed_view = this view's slice [B][H][Wb][C4][8][4];
  * rot_trans = host [B][12].
  */
 int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const float *depth, int per_pixel,
@@ -77,7 +77,7 @@ int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const f
  * (warped*ref).mean(1) :80, similarity_sum/weight_sum :88-93) without ever writing the
  * B x C x D x H x W warped volume.
  *   ref            reference features [B,C,H,W] with element strides (rB,rC,rH,rW)
- *   packed         packed sources [Nsrc][B][C4][H][W][4]
+ *   packed         packed sources [Nsrc][B][H][Wb][C4][8][4]
  *   view_weights   [B][Nsrc][H][W] or NULL
  *   sim_views      [Nsrc][B][D][H][W] per-view similarity (stage 1, feeds PixelwiseNet) or NULL
  *   agg            [B][D][H][W] = sum_i sim_i*w_i / (1e-5 + sum_i w_i)  or NULL (needs view_weights)

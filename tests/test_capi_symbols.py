@@ -36,7 +36,7 @@ def test_version_and_error_strings():
     assert lib.tmvs_error_string(0) == b"ok"
     assert b"NULL" in lib.tmvs_error_string(-1)
     assert lib.tmvs_packed_bytes(4, 1, 32, 288, 400) == 4 * 8 * 288 * 400 * 16
-    assert lib.tmvs_packed_bytes(4, 1, 30, 2, 2) == 4 * 8 * 4 * 16          # C padded to a multiple of 4
+    assert lib.tmvs_packed_bytes(4, 1, 30, 2, 2) == 4 * 2 * 8 * 8 * 16      # C -> 8 groups, W -> one 8-pixel block
 
 
 def test_argument_validation_needs_no_gpu():

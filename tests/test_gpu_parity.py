@@ -38,7 +38,7 @@ def test_homo_warping_channels_last_and_oracle():
     rt = geometry.stage_rot_trans(st.proj_matrix)[0]
     want = oracle.homo_warp(src, rt, st.depth_values)
     packed = ops.pack_sources([cu(src).contiguous(memory_format=torch.channels_last)])
-    got = ops.homo_warp_packed(packed[0], rt, cu(st.depth_values), src.shape[1])
+    got = ops.homo_warp_packed(packed[0], rt, cu(st.depth_values), src.shape[1], src.shape[3])
     assert_costvol_close(got.cpu().numpy(), want, "channels_last")
 
 

@@ -59,7 +59,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
             r[g] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    const float *dep_p = PER_PIXEL ? depth + ((size_t)b * D + d0) * HW + pix : depth + (size_t)b * D + d0;
+    const float *dep_base = PER_PIXEL ? depth + ((size_t)b * D + d0) * HW + pix : depth + (size_t)b * D + d0;
     const int dep_stride = PER_PIXEL ? HW : 1;
     if (AGG) {
 #pragma unroll
@@ -68,6 +68,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     float wsum = 1e-5f;                                // TransMVSNet.py:72
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float xf = (float)x, yf = (float)y;
 
     for (int i = 0; i < n_src; ++i) {
@@ -75,27 +76,28 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
         const TmvsRay ray = tmvs_ray(rt, xf, yf);
         float wi = 0.0f;
         if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
-        const float4 *img = packed + ((size_t)i * b_total + b) * c4 * HW;
+        const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;
         float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
+        const float *dep_p = dep_base;
 #pragma unroll 2
-        for (int k = 0; k < nd; ++k) {
-            const TmvsTaps t = tmvs_taps(ray, rt, __ldg(dep_p + (size_t)k * dep_stride), dims);
+        for (int k = 0; k < nd; ++k, dep_p += dep_stride, out_v += HW) {
+            const TmvsTaps t = tmvs_taps(ray, rt, __ldg(dep_p), dims);
             float s = 0.0f;
             if (t.any) {
                 const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-                const int ya = min(max(t.y0, 0), H - 1) * W, yb = min(max(t.y0 + 1, 0), H - 1) * W;
-                const float4 *p00 = img + (ya + xa);
-                const float4 *p01 = img + (ya + xb);
-                const float4 *p10 = img + (yb + xa);
-                const float4 *p11 = img + (yb + xb);
+                const int ra = min(max(t.y0, 0), H - 1) * pk.row, rb = min(max(t.y0 + 1, 0), H - 1) * pk.row;
+                const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra));
+                const float4 *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
+                const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb));
+                const float4 *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
                 float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
 #pragma unroll
                 for (int g = 0; g < C4T; ++g) {
                     if (EXACT || g < c4) {
-                        const float4 a = ldg4(p00 + (size_t)g * HW);
-                        const float4 bq = ldg4(p01 + (size_t)g * HW);
-                        const float4 cq = ldg4(p10 + (size_t)g * HW);
-                        const float4 dq = ldg4(p11 + (size_t)g * HW);
+                        const float4 a = ldg4(p00 + g * 8);        // + g * 128 bytes: an immediate
+                        const float4 bq = ldg4(p01 + g * 8);
+                        const float4 cq = ldg4(p10 + g * 8);
+                        const float4 dq = ldg4(p11 + g * 8);
                         s00 = dot4(r[g], a, s00);
                         s01 = dot4(r[g], bq, s01);
                         s10 = dot4(r[g], cq, s10);
@@ -109,7 +111,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
                 s += t.ok11 ? t.w11 * s11 : 0.0f;
                 s *= inv_c;                               // .mean(1), TransMVSNet.py:80
             }
-            if (VIEWS) __stcs(out_v + (size_t)k * HW, s);
+            if (VIEWS) __stcs(out_v, s);
             if (AGG) acc_s[k][tid] = __fadd_rn(acc_s[k][tid], __fmul_rn(s, wi));   // TransMVSNet.py:88
         }
         wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
@@ -180,7 +182,7 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
     if (agg && !view_weights) return TMVS_E_NULL;
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
     if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
-    if ((size_t)H * W * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;   // 32-bit offsets inside one view
+    if ((size_t)H * (W + 7) * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;   // 32-bit offsets inside one view
     if (((uintptr_t)packed & 15) != 0) return TMVS_E_ALIGN;
     const int c4 = (C + 3) / 4;
     const int n_dchunks = (D + kDC - 1) / kDC;

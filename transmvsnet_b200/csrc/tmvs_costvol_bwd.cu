@@ -48,7 +48,8 @@ bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ dept
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W);
-    const float4 *img = packed + ((size_t)i * b_total + b) * c4 * HW;
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;
     const float *gp = G + ((size_t)i * b_total + b) * D * HW + pix;
     float4 acc[C4T];
 #pragma unroll
@@ -61,14 +62,14 @@ bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ dept
         const float k00 = t.ok00 ? gw * t.w00 : 0.0f, k01 = t.ok01 ? gw * t.w01 : 0.0f;
         const float k10 = t.ok10 ? gw * t.w10 : 0.0f, k11 = t.ok11 ? gw * t.w11 : 0.0f;
         const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-        const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-        const float4 *p00 = img + (size_t)ya * W + xa, *p01 = img + (size_t)ya * W + xb;
-        const float4 *p10 = img + (size_t)yb * W + xa, *p11 = img + (size_t)yb * W + xb;
+        const int ra = min(max(t.y0, 0), H - 1) * pk.row, rb = min(max(t.y0 + 1, 0), H - 1) * pk.row;
+        const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra)), *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
+        const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb)), *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
 #pragma unroll
         for (int g = 0; g < C4T; ++g) {
             if (EXACT || g < c4) {
-                const float4 a = ldg4(p00 + g * HW), bq = ldg4(p01 + g * HW);
-                const float4 cq = ldg4(p10 + g * HW), dq = ldg4(p11 + g * HW);
+                const float4 a = ldg4(p00 + g * 8), bq = ldg4(p01 + g * 8);
+                const float4 cq = ldg4(p10 + g * 8), dq = ldg4(p11 + g * 8);
                 acc[g].x += k00 * a.x + k01 * bq.x + k10 * cq.x + k11 * dq.x;
                 acc[g].y += k00 * a.y + k01 * bq.y + k10 * cq.y + k11 * dq.y;
                 acc[g].z += k00 * a.z + k01 * bq.z + k10 * cq.z + k11 * dq.z;
@@ -171,7 +172,8 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     const float *rt = geom.rt[i * b_chunk + bl];
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W);
-    const float4 *rimg = refp + (size_t)b * c4 * HW;
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    const float4 *rimg = refp + (size_t)b * pk.slice;
     const float *gview = G + ((size_t)i * b_total + b) * D * HW;
     const int4 *boxes = bbox + (size_t)blockIdx.z * n_tiles * D;
     const int n_pairs = n_tiles * D;
@@ -184,7 +186,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
 #pragma unroll
         for (int g = 0; g < C4T; ++g) {
             if (EXACT || g < c4) {
-                const float4 rv = ldg4(rimg + g * HW + off);
+                const float4 rv = ldg4(tmvs_pk_ptr(rimg, (unsigned)off) + g * 8);
                 acc[g].x = fmaf(k, rv.x, acc[g].x);
                 acc[g].y = fmaf(k, rv.y, acc[g].y);
                 acc[g].z = fmaf(k, rv.z, acc[g].z);
@@ -238,7 +240,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
                 }
             }
             krec[0][tid] = k00; krec[1][tid] = k01; krec[2][tid] = k10; krec[3][tid] = k11;
-            pixrec[tid] = py * W + px;
+            pixrec[tid] = tmvs_pk_off(pk, min(px, W - 1), min(py, H - 1) * pk.row);   // packed word of ref pixel p
             x0rec[tid] = x0; y0rec[tid] = y0;
             for (int c = tid; c < kSlots * kCells; c += kThreads) (&cell[0][0])[c] = kEmpty;
             __syncthreads();
@@ -318,7 +320,7 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     const size_t n_tiles = (size_t)((W + kTX - 1) / kTX) * ((H + kTY - 1) / kTY);
     BwdWorkspace ws;
     ws.ref_packed = 0;
-    ws.partial = align256((size_t)B * ((C + 3) / 4) * HW * 16);
+    ws.partial = align256((size_t)B * tmvs_packed_layout((C + 3) / 4, H, W).slice * 16);
     ws.bbox = ws.partial + align256((size_t)n_src * B * C * HW * 4);
     ws.total = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
     return ws;
@@ -371,7 +373,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     if (!grad_ref && !grad_src) return TMVS_E_NULL;
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
     if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
-    if ((size_t)H * W > 0x7fffffffu) return TMVS_E_SHAPE;
+    if ((size_t)H * (W + 7) * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;
     if (((uintptr_t)packed & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return TMVS_E_ALIGN;
     const BwdWorkspace ws = bwd_layout(B, C, D, H, W, n_src);
     if (workspace_bytes < ws.total) return TMVS_E_SHAPE;

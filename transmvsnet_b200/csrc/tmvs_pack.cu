@@ -33,7 +33,8 @@ pack_sources_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
         const int c = 4 * g + j;
         v[j] = (c < C) ? __ldg(base + c * sC) : 0.0f;
     }
-    packed[((size_t)vb * c4 + g) * HW + p] = make_float4(v[0], v[1], v[2], v[3]);
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    packed[(size_t)vb * pk.slice + tmvs_pk_off(pk, x, y * pk.row) + g * 8] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // NCHW fast path (x contiguous, W % 4 == 0, 16-byte aligned rows): one thread moves a 4-pixel x 4-channel
@@ -57,7 +58,8 @@ pack_sources_nchw4_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float
         const int c = 4 * g + j;
         v[j] = (c < C) ? __ldg(reinterpret_cast<const float4 *>(base + c * sC)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float4 *o = packed + ((size_t)vb * c4 + g) * H * W + (size_t)y * W + 4 * xq;
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    float4 *o = packed + (size_t)vb * pk.slice + tmvs_pk_off(pk, 4 * xq, y * pk.row) + g * 8;   // 4 | 8: same block
     o[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
     o[1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
     o[2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
@@ -77,7 +79,8 @@ pack_sources_nhwc_kernel(SrcPtrs src, int64_t sB, int64_t sH, int64_t sW, float4
     const int view = vb / B, b = vb - view * B;
     const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
     const float *base = src.p[view] + b * sB + y * sH + x * sW + 4 * g;
-    packed[((size_t)vb * c4 + g) * HW + p] = __ldg(reinterpret_cast<const float4 *>(base));
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    packed[(size_t)vb * pk.slice + tmvs_pk_off(pk, x, y * pk.row) + g * 8] = __ldg(reinterpret_cast<const float4 *>(base));
 }
 
 constexpr int kWarpDC = 4;   // depth planes per thread in the drop-in warp
@@ -99,7 +102,8 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
     const float *rt = geom.rt[bl];
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const TmvsDims dims = tmvs_dims(H, W);
-    const float4 *img = packed + (size_t)b * c4 * HW;
+    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
+    const float4 *img = packed + (size_t)b * pk.slice;
 #pragma unroll
     for (int k = 0; k < kWarpDC; ++k) {
         const int d = d0 + k;
@@ -113,14 +117,14 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
             continue;
         }
         const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-        const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-        const float4 *p00 = img + (size_t)ya * W + xa;
-        const float4 *p01 = img + (size_t)ya * W + xb;
-        const float4 *p10 = img + (size_t)yb * W + xa;
-        const float4 *p11 = img + (size_t)yb * W + xb;
+        const int ra = min(max(t.y0, 0), H - 1) * pk.row, rb = min(max(t.y0 + 1, 0), H - 1) * pk.row;
+        const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra));
+        const float4 *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
+        const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb));
+        const float4 *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
         for (int g = 0; g < c4; ++g) {
-            const float4 a = ldg4(p00 + g * HW), bq = ldg4(p01 + g * HW);
-            const float4 cq = ldg4(p10 + g * HW), dq = ldg4(p11 + g * HW);
+            const float4 a = ldg4(p00 + g * 8), bq = ldg4(p01 + g * 8);
+            const float4 cq = ldg4(p10 + g * 8), dq = ldg4(p11 + g * 8);
             float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {bq.x, bq.y, bq.z, bq.w};
             float vc[4] = {cq.x, cq.y, cq.z, cq.w}, vd[4] = {dq.x, dq.y, dq.z, dq.w};
 #pragma unroll
@@ -145,7 +149,7 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
 extern "C" size_t tmvs_packed_bytes(int n_src, int B, int C, int H, int W)
 {
     if (n_src <= 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-    return (size_t)n_src * B * ((C + 3) / 4) * H * W * 4 * sizeof(float);
+    return (size_t)n_src * B * tmvs_packed_layout((C + 3) / 4, H, W).slice * 4 * sizeof(float);
 }
 
 extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,

@@ -57,13 +57,13 @@ def _feature_strides(feats: Sequence[torch.Tensor]) -> Tuple[int, int, int, int]
 
 
 def pack_sources(src_feas: Sequence[torch.Tensor]) -> torch.Tensor:
-    """N x [B,C,H,W] (any common strides) -> packed [N,B,C4,H,W,4] (kernel-native layout)."""
+    """N x [B,C,H,W] (any common strides) -> packed [N,B,H,Wb,C4,8,4] (kernel-native blocked channel-last)."""
     lib = _lib.load()
     dev = _need_cuda(*src_feas)
     b, c, h, w = src_feas[0].shape
     n = len(src_feas)
     sb, sc, sh, sw = _feature_strides(src_feas)
-    packed = torch.empty((n, b, (c + 3) // 4, h, w, 4), dtype=torch.float32, device=dev)
+    packed = torch.empty((n, b, h, (w + 7) // 8, (c + 3) // 4, 8, 4), dtype=torch.float32, device=dev)
     ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in src_feas])
     with torch.cuda.device(dev):
         rc = lib.tmvs_pack_sources(ctypes.cast(ptrs, ctypes.c_void_p), n, sb, sc, sh, sw, _ptr(packed),
@@ -80,10 +80,12 @@ def _depth_mode(depth_values: torch.Tensor, b: int, h: int, w: int) -> int:
     raise _lib.TmvsError(f"depth_values must be [B,D] or [B,D,{h},{w}], got {tuple(depth_values.shape)}")
 
 
-def homo_warp_packed(packed_view: torch.Tensor, rot_trans, depth_values: torch.Tensor, channels: int) -> torch.Tensor:
+def homo_warp_packed(packed_view: torch.Tensor, rot_trans, depth_values: torch.Tensor, channels: int,
+                     width: int) -> torch.Tensor:
+    """packed_view: one view's slice [B,H,Wb,C4,8,4] of pack_sources(); width = the unpadded W."""
     lib = _lib.load()
     dev = _need_cuda(packed_view, depth_values)
-    b, c4, h, w, _ = packed_view.shape
+    b, h, w = packed_view.shape[0], packed_view.shape[1], width
     d = depth_values.shape[1]
     mode = _depth_mode(depth_values, b, h, w)
     depth_values = depth_values.contiguous()
@@ -106,7 +108,7 @@ def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.
     with torch.no_grad():
         rt = relative_rot_trans(src_proj.float(), ref_proj.float())
         packed = pack_sources([src_fea.detach()])
-        return homo_warp_packed(packed[0], rt, depth_values.detach(), src_fea.shape[1])
+        return homo_warp_packed(packed[0], rt, depth_values.detach(), src_fea.shape[1], src_fea.shape[3])
 
 
 def cost_volume_packed(ref_fea: torch.Tensor, packed: torch.Tensor, rot_trans, depth_values: torch.Tensor,
