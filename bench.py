@@ -25,6 +25,13 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 WORKLOADS = {
     # BASELINE.json configs[1]: DTU test cascade 1152x1600, N=5, depths 48/32/8
@@ -136,8 +143,7 @@ def run_reference_arm(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))          # bounded: each step is seconds of CPU work
-    warmup = 1 if args.warmup > 0 else 0
+    steps, warmup = max(1, args.steps), max(0, args.warmup)   # exactly K timed steps; each is a bounded sample
     vv, times, cores, sample = cpu_hot_path_time(workload, steps, warmup)
     total = sum(times)
     value = vv * len(times) / total
@@ -148,9 +154,8 @@ def run_reference_arm(args, workload):
         "config": {"workload": workload["name"], "timed_sample": sample},
         "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxel-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "requested_steps": args.steps,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -312,12 +317,18 @@ def run_tmvs_arm(args, workload):
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # exactly ONE line may reach stdout (the JSON): libraries such as NCCL print banners there, so fd 1 is
+    # pointed at stderr for the run and the JSON line is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     workload = WORKLOADS[args.workload]
     if args.impl == "reference":

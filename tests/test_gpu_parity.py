@@ -88,6 +88,18 @@ def test_cost_volume_stage_shapes_vs_oracle():
         assert_costvol_close(agg.cpu().numpy(), o_agg, f"stage {stage}")
 
 
+def test_cost_volume_full_size_stage3_vs_oracle():
+    """BASELINE config-2 stage-3 size (1152x1600, the hardest case for fp32 coordinate rounding: ulp(1600) ~ 1e-4 px)
+    against the CPU oracle, at the north_star tolerance."""
+    st = synthetic.make_stage(3, batch=1, n_views=3, height=1152, width=1600, seed=7)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values,
+                                  st.view_weights, want_views=False)
+    agg, _ = tm.cost_volume(cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(st.depth_values),
+                            cu(st.view_weights))
+    assert_costvol_close(agg.cpu().numpy(), o_agg, "full-size stage 3")
+
+
 def test_cost_volume_linearity_full_size():
     """Size-independent property at the BASELINE config-2 stage-3 size: the volume is linear in the source
     features and in the reference features (checked without a CPU oracle)."""

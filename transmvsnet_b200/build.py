@@ -57,14 +57,50 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# kernels whose full SASS is committed (the hot instantiations); every other kernel gets an opcode histogram
+HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1E", "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1E",
+               "costvol_fwd_kernelILi2ELb1ELb1ELb0ELb1E", "costvol_fwd_kernelILi8ELb1ELb1ELb1ELb0E",
+               "pack_sources_nchw4_kernel", "homo_warp_fwd_kernelILb1E", "softmax_wta_kernelILi48E",
+               "softmax_wta_kernelILi32E", "softmax_wta_kernelILi8E", "depth_wta_kernel",
+               "bwd_src_kernelILi8ELb1ELb1E", "bwd_ref_kernelILi8ELb1ELb1E", "bwd_bbox_kernelILb1E",
+               "costvol_tma_kernel")
+
+
 def dump_sass(out_dir: str) -> None:
-    """Write one SASS listing per translation unit (committed under profiles/sass/)."""
+    """Compact SASS evidence under profiles/sass/: full listings (encodings stripped) of the hot kernels and a
+    per-kernel opcode histogram of everything in the library."""
+    import collections
+    import re
     os.makedirs(out_dir, exist_ok=True)
+    hist_lines = []
     for src in SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         res = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True)
+        keep, name, ops, hot = [], None, None, False
+        for line in res.stdout.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                if name:
+                    hist_lines.append(f"{name}: " + " ".join(f"{o}={c}" for o, c in ops.most_common(14)))
+                name, ops = m.group(1), collections.Counter()
+                hot = any(h in name for h in HOT_KERNELS)
+                if hot:
+                    keep.append("\n" + line.strip())
+                continue
+            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", line)
+            if m and name:
+                ins = m.group(2).strip()
+                toks = ins.split()
+                op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+                ops[op.split(".")[0]] += 1
+                if hot:
+                    keep.append(f"  /*{m.group(1)}*/ {ins} ;")
+        if name:
+            hist_lines.append(f"{name}: " + " ".join(f"{o}={c}" for o, c in ops.most_common(14)))
         with open(os.path.join(out_dir, src.replace(".cu", ".sass")), "w") as f:
-            f.write(res.stdout)
+            f.write("\n".join(keep) + "\n")
+    with open(os.path.join(out_dir, "opcode_histogram.txt"), "w") as f:
+        f.write("\n".join(hist_lines) + "\n")
 
 
 if __name__ == "__main__":
