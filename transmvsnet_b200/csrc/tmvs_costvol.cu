@@ -10,7 +10,15 @@
 // supplies the cross-plane reuse.  The channel reduction is an in-register dot product taken
 // BEFORE the bilinear blend ("dot first": 4 dots of C, then 4 scalar weights), which is the
 // same sum as the reference's blend-then-multiply up to fp32 re-association.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tmvs_common.cuh"
+
+// TMA-staged variant (tmvs_costvol_tma.cu); TMVS_E_UNSUPPORTED when it does not apply
+int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *packed,
+                         const float *rot_trans, const float *depth, int per_pixel, const float *view_weights,
+                         float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, cudaStream_t st);
 
 namespace {
 
@@ -188,6 +196,14 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
     const int n_dchunks = (D + kDC - 1) / kDC;
     const int b_per_launch = TMVS_GEOM_SLOTS / n_src;       // rot/trans ride in the parameter bank
     cudaStream_t st = (cudaStream_t)stream;
+    // Default: shared-memory tiles staged by TMA.  TMVS_COSTVOL_PATH=l1 selects the L1-cached global gather
+    // (same arithmetic; also the automatic choice when C/4 is not 2, 4 or 8).
+    const char *path = getenv("TMVS_COSTVOL_PATH");
+    if (!(path && strcmp(path, "l1") == 0)) {
+        int rc = tmvs_costvol_fwd_tma(ref, rB, rC, rH, rW, packed, rot_trans, depth, per_pixel, view_weights, sim_views,
+                                      agg, B, C, D, H, W, n_src, st);
+        if (rc != TMVS_E_UNSUPPORTED) return rc;
+    }
     dim3 block(kTileX, kTileY);
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
