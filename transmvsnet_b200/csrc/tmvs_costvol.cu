@@ -196,10 +196,13 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
     const int n_dchunks = (D + kDC - 1) / kDC;
     const int b_per_launch = TMVS_GEOM_SLOTS / n_src;       // rot/trans ride in the parameter bank
     cudaStream_t st = (cudaStream_t)stream;
-    // Default: shared-memory tiles staged by TMA.  TMVS_COSTVOL_PATH=l1 selects the L1-cached global gather
-    // (same arithmetic; also the automatic choice when C/4 is not 2, 4 or 8).
+    // Default: the L1-cached global gather below.  TMVS_COSTVOL_PATH=tma selects the TMA-staged shared-memory
+    // variant (tmvs_costvol_tma.cu; same arithmetic, bit-identical results).  It is opt-in because on the
+    // BASELINE workloads it measured slower (profiles/README.md): its windows must be re-derived per
+    // (tile, view, plane span) from per-pixel hypotheses, and the barrier + copy latency that costs is not
+    // hidden at 2-4 CTAs per SM.
     const char *path = getenv("TMVS_COSTVOL_PATH");
-    if (!(path && strcmp(path, "l1") == 0)) {
+    if (path && strcmp(path, "tma") == 0) {
         int rc = tmvs_costvol_fwd_tma(ref, rB, rC, rH, rW, packed, rot_trans, depth, per_pixel, view_weights, sim_views,
                                       agg, B, C, D, H, W, n_src, st);
         if (rc != TMVS_E_UNSUPPORTED) return rc;

@@ -3,8 +3,9 @@
 // Same arithmetic as costvol_fwd_kernel (tmvs_costvol.cu) -- replaces models/TransMVSNet.py:71-93 -- but the
 // bilinear taps are read from SHARED MEMORY: adjacent depth planes map to neighbouring source pixels, so the
 // footprint of a 32x8 reference tile over an 8-plane chunk is a small source window.  Per (CTA, view):
-//   pass 1  every thread computes its 8 sample positions (the reference's arithmetic, tmvs_coords) and the
-//           CTA reduces the exact bounding box of all in-bounds taps (REDUX + one barrier);
+//   pass 1  every thread computes its 8 sample positions (the reference's arithmetic, tmvs_coords), parks them in
+//           shared memory, and the CTA reduces the exact bounding boxes of the in-bounds taps of the next
+//           8 / 4 / 2 / 1 planes (REDUX + one barrier) and takes the longest span whose box fits a window;
 //   load    one elected thread issues ONE TMA tensor copy (cp.async.bulk.tensor.4d, SASS UTMALDG) of the box
 //           [rows][8-px blocks][C4][8 px x 4 ch] from the packed layout into shared memory and the CTA waits
 //           on the mbarrier the copy completes on.  The box shape is picked from a small menu of tensor maps
@@ -22,14 +23,15 @@ namespace {
 
 constexpr int kTileX = 32, kTileY = 8, kThreads = kTileX * kTileY;
 constexpr int kDC = 8;
-constexpr int kCapBlocks = 96;       // 8-pixel blocks (all channel groups) the shared-memory window holds
+constexpr int kCapBlocks = 80;       // 8-pixel blocks (all channel groups) the shared-memory window holds
 constexpr int kMenu = 5;
+constexpr int kSpans = 4;            // plane spans tried per load: all remaining, 4, 2, 1
 constexpr int kEmpty = 0x7fffffff;
 // window shapes (8-px blocks wide x rows high), tried in order: typical first, then wide / tall variants
 __constant__ int c_menu_bw[kMenu] = {7, 8, 10, 6, 5};
-__constant__ int c_menu_bh[kMenu] = {10, 12, 9, 16, 19};
+__constant__ int c_menu_bh[kMenu] = {10, 10, 8, 13, 16};
 const int h_menu_bw[kMenu] = {7, 8, 10, 6, 5};
-const int h_menu_bh[kMenu] = {10, 12, 9, 16, 19};
+const int h_menu_bh[kMenu] = {10, 10, 8, 13, 16};
 
 struct TmvsTmaMaps {
     CUtensorMap m[kMenu];
@@ -79,14 +81,13 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
                    int D, int H, int W, int n_src, int n_dchunks, const __grid_constant__ TmvsGeom geom,
                    const __grid_constant__ TmvsTmaMaps maps)
 {
-    constexpr bool KEEP = C4T <= 4;                    // sample positions parked in shared memory (else recomputed)
     constexpr int kTileWords = kCapBlocks * C4T * 8;   // float4 words
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
-    float *acc_s = reinterpret_cast<float *>(smem_raw + (size_t)kTileWords * 16);          // [kDC][kThreads]
-    float *crd_s = acc_s + (AGG ? kDC * kThreads : 0);                                      // [2][kDC][kThreads]
-    int *red_all = reinterpret_cast<int *>(crd_s + (KEEP ? 2 * kDC * kThreads : 0));        // [2][4][kTileY]
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(red_all + 2 * 4 * kTileY);
+    float *crd_s = reinterpret_cast<float *>(smem_raw + (size_t)kTileWords * 16);          // [2][kDC][kThreads]
+    int *red_all = reinterpret_cast<int *>(crd_s + 2 * kDC * kThreads);                    // [2][kSpans*4][kTileY]
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(red_all + 2 * kSpans * 4 * kTileY);
+    float *acc_s = reinterpret_cast<float *>(bar + 2);                                     // [kDC][kThreads] (AGG)
 
     const int tid = threadIdx.y * kTileX + threadIdx.x;
     const int chunk = blockIdx.x % n_dchunks;
@@ -130,7 +131,7 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     const TmvsDims dims = tmvs_dims(H, W);
     const TmvsPacked pk = tmvs_packed_layout(C4T, H, W);
     const float xf = (float)x, yf = (float)y;
-    unsigned phase = 0;
+    unsigned phase = 0, round = 0;
     __syncthreads();                                   // mbarrier initialised
 
     for (int i = 0; i < n_src; ++i) {
@@ -138,119 +139,151 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
         const TmvsRay ray = tmvs_ray(rt, xf, yf);
         float wi = 0.0f;
         if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
+        const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;     // global path (window too large)
+        float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
 
-        int *red = red_all + (i & 1) * 4 * kTileY;     // double-buffered: a fast warp may already be in the next view
-        // ---- pass 1: sample positions + bounding box of the in-bounds taps of this (tile, chunk, view)
-        int lo_x = kEmpty, lo_y = kEmpty, hi_x = -1, hi_y = -1;
+        // ---- pass 1: the sample positions of this thread's planes (the reference's arithmetic), parked in smem
         if (active) {
             const float *dep_p = dep_base;
 #pragma unroll 2
             for (int k = 0; k < nd; ++k, dep_p += dep_stride) {
                 const float2 c = tmvs_coords(ray, rt, __ldg(dep_p), dims);
-                if (KEEP) {
-                    crd_s[k * kThreads + tid] = c.x;
-                    crd_s[(kDC + k) * kThreads + tid] = c.y;
-                }
-                const int x0 = (int)floorf(c.x), y0 = (int)floorf(c.y);
-                const bool xin = ((unsigned)x0 < (unsigned)W) | ((unsigned)(x0 + 1) < (unsigned)W);
-                const bool yin = ((unsigned)y0 < (unsigned)H) | ((unsigned)(y0 + 1) < (unsigned)H);
-                if (xin & yin) {
-                    lo_x = min(lo_x, max(x0, 0)); hi_x = max(hi_x, min(x0 + 1, W - 1));
-                    lo_y = min(lo_y, max(y0, 0)); hi_y = max(hi_y, min(y0 + 1, H - 1));
-                }
+                crd_s[k * kThreads + tid] = c.x;
+                crd_s[(kDC + k) * kThreads + tid] = c.y;
             }
         }
-        lo_x = __reduce_min_sync(0xffffffffu, lo_x);
-        lo_y = __reduce_min_sync(0xffffffffu, lo_y);
-        hi_x = __reduce_max_sync(0xffffffffu, hi_x);
-        hi_y = __reduce_max_sync(0xffffffffu, hi_y);
-        if (threadIdx.x == 0) {
-            red[0 * kTileY + threadIdx.y] = lo_x; red[1 * kTileY + threadIdx.y] = lo_y;
-            red[2 * kTileY + threadIdx.y] = hi_x; red[3 * kTileY + threadIdx.y] = hi_y;
-        }
-        __syncthreads();        // box parts visible; every thread is also done with the previous view's tile
-        lo_x = kEmpty; lo_y = kEmpty; hi_x = -1; hi_y = -1;
-#pragma unroll
-        for (int w = 0; w < kTileY; ++w) {
-            lo_x = min(lo_x, red[0 * kTileY + w]); lo_y = min(lo_y, red[1 * kTileY + w]);
-            hi_x = max(hi_x, red[2 * kTileY + w]); hi_y = max(hi_y, red[3 * kTileY + w]);
-        }
-        const bool empty = hi_x < 0;                    // no tap of the whole tile lands inside the source image
-        const int bx0 = lo_x >> 3, by0 = lo_y;
-        const int nbx = (hi_x >> 3) - bx0 + 1, nby = hi_y - by0 + 1;
-        int shape = -1;
-        if (!empty) {
-#pragma unroll
-            for (int s = kMenu - 1; s >= 0; --s)
-                if (nbx <= c_menu_bw[s] && nby <= c_menu_bh[s]) shape = s;
-        }
-        const int bw = shape >= 0 ? c_menu_bw[shape] : 0;
-        if (shape >= 0) {
-            if (tid == 0) {
-                mbar_expect_tx(bar, (unsigned)(bw * c_menu_bh[shape] * C4T * 128));
-                tma_load_4d(tile, &maps.m[shape], bar, 0, 0, bx0, ((i * b_total + b) * H) + by0);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-        }
-        const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;     // global path (window too large)
-        const int tile_base = -(by0 * bw + bx0) * (C4T * 8);
 
-        // ---- pass 2: taps from shared memory (or from global memory if the window did not fit)
-        if (active) {
-            float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
-            const float *dep_p = dep_base;
-#pragma unroll 2
-            for (int k = 0; k < nd; ++k, dep_p += dep_stride, out_v += HW) {
-                float s = 0.0f;
-                if (!empty) {
-                    float2 c;
-                    if (KEEP) c = make_float2(crd_s[k * kThreads + tid], crd_s[(kDC + k) * kThreads + tid]);
-                    else c = tmvs_coords(ray, rt, __ldg(dep_p), dims);
-                    const TmvsTaps t = tmvs_footprint(c.x, c.y, dims);
-                    if (t.any) {
-                        const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-                        const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-                        float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
-                        if (shape >= 0) {
-                            const int ra = ya * bw * (C4T * 8) + tile_base, rb = yb * bw * (C4T * 8) + tile_base;
-                            const int ca = (xa >> 3) * (C4T * 8) + (xa & 7), cb = (xb >> 3) * (C4T * 8) + (xb & 7);
-                            const float4 *p00 = tile + (ra + ca), *p01 = tile + (ra + cb);
-                            const float4 *p10 = tile + (rb + ca), *p11 = tile + (rb + cb);
+        // ---- the planes are consumed in spans: as many as fit one shared-memory window (all 8 for the usual
+        //      geometry; 4, 2 or 1 when the epipolar walk is long or diagonal)
+        int k0 = 0;
+        while (k0 < nd) {
+            const int rem = nd - k0;
+            const int span_len[kSpans] = {rem, min(rem, 4), min(rem, 2), 1};
+            int lo_x[kSpans], lo_y[kSpans], hi_x[kSpans], hi_y[kSpans];
 #pragma unroll
-                            for (int g = 0; g < C4T; ++g) {
-                                const float4 a = p00[g * 8], bq = p01[g * 8], cq = p10[g * 8], dq = p11[g * 8];
-                                s00 = dot4(r[g], a, s00);
-                                s01 = dot4(r[g], bq, s01);
-                                s10 = dot4(r[g], cq, s10);
-                                s11 = dot4(r[g], dq, s11);
-                            }
-                        } else {
-                            const int ra = ya * pk.row, rb = yb * pk.row;
-                            const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra));
-                            const float4 *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
-                            const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb));
-                            const float4 *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
+            for (int sp = 0; sp < kSpans; ++sp) { lo_x[sp] = kEmpty; lo_y[sp] = kEmpty; hi_x[sp] = -1; hi_y[sp] = -1; }
+            if (active) {
+                for (int k = 0; k < rem; ++k) {
+                    const float cx = crd_s[(k0 + k) * kThreads + tid], cy = crd_s[(kDC + k0 + k) * kThreads + tid];
+                    const int x0 = (int)floorf(cx), y0 = (int)floorf(cy);
+                    const bool xin = ((unsigned)x0 < (unsigned)W) | ((unsigned)(x0 + 1) < (unsigned)W);
+                    const bool yin = ((unsigned)y0 < (unsigned)H) | ((unsigned)(y0 + 1) < (unsigned)H);
+                    if (xin & yin) {
+                        const int ax = max(x0, 0), bx = min(x0 + 1, W - 1), ay = max(y0, 0), by = min(y0 + 1, H - 1);
 #pragma unroll
-                            for (int g = 0; g < C4T; ++g) {
-                                const float4 a = ldg4(p00 + g * 8), bq = ldg4(p01 + g * 8);
-                                const float4 cq = ldg4(p10 + g * 8), dq = ldg4(p11 + g * 8);
-                                s00 = dot4(r[g], a, s00);
-                                s01 = dot4(r[g], bq, s01);
-                                s10 = dot4(r[g], cq, s10);
-                                s11 = dot4(r[g], dq, s11);
+                        for (int sp = 0; sp < kSpans; ++sp) {
+                            if (k < span_len[sp]) {
+                                lo_x[sp] = min(lo_x[sp], ax); hi_x[sp] = max(hi_x[sp], bx);
+                                lo_y[sp] = min(lo_y[sp], ay); hi_y[sp] = max(hi_y[sp], by);
                             }
                         }
-                        s = t.ok00 ? t.w00 * s00 : 0.0f;
-                        s += t.ok01 ? t.w01 * s01 : 0.0f;
-                        s += t.ok10 ? t.w10 * s10 : 0.0f;
-                        s += t.ok11 ? t.w11 * s11 : 0.0f;
-                        s *= inv_c;                               // .mean(1), TransMVSNet.py:80
                     }
                 }
-                if (VIEWS) __stcs(out_v, s);
-                if (AGG) acc_s[k * kThreads + tid] = __fadd_rn(acc_s[k * kThreads + tid], __fmul_rn(s, wi));   // :88
             }
+            int *red = red_all + (round & 1u) * (kSpans * 4 * kTileY);   // double-buffered across rounds
+            ++round;
+#pragma unroll
+            for (int sp = 0; sp < kSpans; ++sp) {
+                const int a = __reduce_min_sync(0xffffffffu, lo_x[sp]), bq = __reduce_min_sync(0xffffffffu, lo_y[sp]);
+                const int c = __reduce_max_sync(0xffffffffu, hi_x[sp]), dq = __reduce_max_sync(0xffffffffu, hi_y[sp]);
+                if (threadIdx.x == 0) {
+                    red[(sp * 4 + 0) * kTileY + threadIdx.y] = a; red[(sp * 4 + 1) * kTileY + threadIdx.y] = bq;
+                    red[(sp * 4 + 2) * kTileY + threadIdx.y] = c; red[(sp * 4 + 3) * kTileY + threadIdx.y] = dq;
+                }
+            }
+            __syncthreads();    // boxes visible; every thread is also done reading the previous window
+            int span = 1, shape = -1, bx0 = 0, by0 = 0;
+            bool empty = true;
+            {
+                bool chosen = false;
+#pragma unroll
+                for (int sp = 0; sp < kSpans; ++sp) {
+                    int ax = kEmpty, ay = kEmpty, cx = -1, cy = -1;
+#pragma unroll
+                    for (int w = 0; w < kTileY; ++w) {
+                        ax = min(ax, red[(sp * 4 + 0) * kTileY + w]); ay = min(ay, red[(sp * 4 + 1) * kTileY + w]);
+                        cx = max(cx, red[(sp * 4 + 2) * kTileY + w]); cy = max(cy, red[(sp * 4 + 3) * kTileY + w]);
+                    }
+                    if (!chosen) {
+                        const bool emp = cx < 0;           // no tap of the whole tile lands inside the source image
+                        int fit = -1;
+                        if (!emp) {
+                            const int nbx = (cx >> 3) - (ax >> 3) + 1, nby = cy - ay + 1;
+#pragma unroll
+                            for (int m = kMenu - 1; m >= 0; --m)
+                                if (nbx <= c_menu_bw[m] && nby <= c_menu_bh[m]) fit = m;
+                        }
+                        if (emp || fit >= 0 || sp == kSpans - 1) {     // the last span (1 plane) may take the global path
+                            chosen = true;
+                            span = span_len[sp]; shape = fit; empty = emp;
+                            bx0 = emp ? 0 : (ax >> 3); by0 = emp ? 0 : ay;
+                        }
+                    }
+                }
+            }
+            const int bw = shape >= 0 ? c_menu_bw[shape] : 0;
+            if (shape >= 0) {
+                if (tid == 0) {
+                    mbar_expect_tx(bar, (unsigned)(bw * c_menu_bh[shape] * C4T * 128));
+                    tma_load_4d(tile, &maps.m[shape], bar, 0, 0, bx0, ((i * b_total + b) * H) + by0);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+            const int tile_base = -(by0 * bw + bx0) * (C4T * 8);
+
+            // ---- pass 2: taps from shared memory (or from global memory if even one plane's window is too large)
+            if (active) {
+#pragma unroll 2
+                for (int k = k0; k < k0 + span; ++k) {
+                    float s = 0.0f;
+                    if (!empty) {
+                        const TmvsTaps t = tmvs_footprint(crd_s[k * kThreads + tid], crd_s[(kDC + k) * kThreads + tid], dims);
+                        if (t.any) {
+                            const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+                            const int ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+                            float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+                            if (shape >= 0) {
+                                const int ra = ya * bw * (C4T * 8) + tile_base, rb = yb * bw * (C4T * 8) + tile_base;
+                                const int ca = (xa >> 3) * (C4T * 8) + (xa & 7), cb = (xb >> 3) * (C4T * 8) + (xb & 7);
+                                const float4 *p00 = tile + (ra + ca), *p01 = tile + (ra + cb);
+                                const float4 *p10 = tile + (rb + ca), *p11 = tile + (rb + cb);
+#pragma unroll
+                                for (int g = 0; g < C4T; ++g) {
+                                    const float4 a = p00[g * 8], bq = p01[g * 8], cq = p10[g * 8], dq = p11[g * 8];
+                                    s00 = dot4(r[g], a, s00);
+                                    s01 = dot4(r[g], bq, s01);
+                                    s10 = dot4(r[g], cq, s10);
+                                    s11 = dot4(r[g], dq, s11);
+                                }
+                            } else {
+                                const int ra = ya * pk.row, rb = yb * pk.row;
+                                const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra));
+                                const float4 *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
+                                const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb));
+                                const float4 *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
+#pragma unroll
+                                for (int g = 0; g < C4T; ++g) {
+                                    const float4 a = ldg4(p00 + g * 8), bq = ldg4(p01 + g * 8);
+                                    const float4 cq = ldg4(p10 + g * 8), dq = ldg4(p11 + g * 8);
+                                    s00 = dot4(r[g], a, s00);
+                                    s01 = dot4(r[g], bq, s01);
+                                    s10 = dot4(r[g], cq, s10);
+                                    s11 = dot4(r[g], dq, s11);
+                                }
+                            }
+                            s = t.ok00 ? t.w00 * s00 : 0.0f;
+                            s += t.ok01 ? t.w01 * s01 : 0.0f;
+                            s += t.ok10 ? t.w10 * s10 : 0.0f;
+                            s += t.ok11 ? t.w11 * s11 : 0.0f;
+                            s *= inv_c;                               // .mean(1), TransMVSNet.py:80
+                        }
+                    }
+                    if (VIEWS) __stcs(out_v + (size_t)k * HW, s);
+                    if (AGG) acc_s[k * kThreads + tid] = __fadd_rn(acc_s[k * kThreads + tid], __fmul_rn(s, wi));   // :88
+                }
+            }
+            k0 += span;
         }
         wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
     }
@@ -282,8 +315,8 @@ EncodeTiledFn encode_tiled_fn()
 template <int C4T>
 constexpr size_t tma_smem_bytes(bool agg)
 {
-    return (size_t)kCapBlocks * C4T * 128 + (agg ? kDC * kThreads * 4 : 0) + (C4T <= 4 ? 2 * kDC * kThreads * 4 : 0) +
-           2 * 4 * kTileY * 4 + 16;
+    return (size_t)kCapBlocks * C4T * 128 + 2 * kDC * kThreads * 4 + 2 * kSpans * 4 * kTileY * 4 + 16 +
+           (agg ? kDC * kThreads * 4 : 0);
 }
 
 template <int C4T, bool PER_PIXEL>
