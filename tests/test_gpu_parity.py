@@ -11,7 +11,7 @@ import torch
 from conftest import (COSTVOL_REL, DEPTH_FRAC, DEPTHNET_GIVEN, PROB_ABS, WARP_CASES, assert_costvol_close, golden,
                       rel_err)
 import transmvsnet_b200 as tm
-from transmvsnet_b200 import geometry, ops, synthetic
+from transmvsnet_b200 import geometry, ops, pipeline, synthetic
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -157,6 +157,65 @@ def test_identity_cameras_full_size_stage1():
     for d in (0, 17, 47):
         e_max, e_l2 = rel_err(got[:, d].cpu().numpy(), want.cpu().numpy())
         assert e_max <= COSTVOL_REL and e_l2 <= COSTVOL_REL, (d, e_max, e_l2)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs 3-5 as parity cases
+@pytest.mark.parametrize("n_views", [3, 5, 11])
+@pytest.mark.parametrize("channels", [8, 16, 32])
+@pytest.mark.parametrize("depths", [48, 96, 192])
+def test_config5_sweep_vs_oracle(depths, channels, n_views):
+    """configs[4]: D x C x N sweep (small map so the oracle takes a fraction of a second per case)."""
+    st = synthetic.make_stage(1, batch=1, n_views=n_views, height=96, width=160, channels=channels,
+                              num_depth=depths, seed=depths + channels + n_views)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values,
+                                  st.view_weights, want_views=False)
+    agg, _ = tm.cost_volume(cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(st.depth_values),
+                            cu(st.view_weights))
+    assert_costvol_close(agg.cpu().numpy(), o_agg, f"D={depths} C={channels} N={n_views}")
+    _, idx, dep, conf = tm.softmax_wta(cu(st.logits), cu(st.depth_values), want_prob=False)
+    _, o_idx, o_dep, o_conf = oracle.softmax_wta(st.logits, st.depth_values, want_prob=False)
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(dep.cpu().numpy(), o_dep)
+    assert np.abs(conf.cpu().numpy() - o_conf).max() <= PROB_ABS
+
+
+def test_config3_tnt_shaped_vs_oracle():
+    """configs[2]: Tanks&Temples-shaped cameras (fx=fy=0.6W, depth 0.5-10), N=7, at 1/4 x 1/4 of 1056x1920."""
+    for st in synthetic.make_cascade(batch=1, n_views=7, height=264, width=480, kind="unit", seed=21):
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values,
+                                      st.view_weights, want_views=False)
+        out = pipeline.run_stage(pipeline.stage_to_device(st, DEV))
+        assert_costvol_close(out["similarity"].cpu().numpy(), o_agg, f"T&T-shaped stage {st.stage}")
+        _, o_idx, o_dep, _ = oracle.softmax_wta(st.logits, st.depth_values, want_prob=False)
+        assert np.array_equal(out["index"].cpu().numpy(), o_idx) and np.array_equal(out["depth"].cpu().numpy(), o_dep)
+
+
+def test_config4_blendedmvs_batch8_forward_backward():
+    """configs[3]: BlendedMVS-shaped N=7, batch 8, forward + atomic-free backward; 1/4-size maps against the
+    oracle, then one full-size (576x768) batch-8 stage executed twice for bit-reproducibility."""
+    st = synthetic.make_stage(2, batch=8, n_views=7, height=144, width=192, kind="unit", seed=31)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    feats = [cu(f).requires_grad_(True) for f in st.features]
+    agg, _ = tm.cost_volume(feats[0], feats[1:], rt, cu(st.depth_values), cu(st.view_weights))
+    g = torch.randn(agg.shape, generator=torch.Generator().manual_seed(1))
+    agg.backward(cu(g))
+    vw = st.view_weights
+    coef = (vw / (1e-5 + vw.sum(1, keepdim=True))).permute(1, 0, 2, 3)
+    gviews = (g[None] * coef[:, :, None]).contiguous()
+    _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, vw, want_views=False)
+    o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, gviews)
+    assert_costvol_close(agg.detach().cpu().numpy(), o_agg, "B=8 forward")
+    assert_costvol_close(feats[0].grad.cpu().numpy(), o_ref, "B=8 grad_ref")
+    assert_costvol_close(torch.stack([f.grad for f in feats[1:]], 0).cpu().numpy(), o_src, "B=8 grad_src")
+    big = synthetic.make_stage(3, batch=8, n_views=7, height=576, width=768, kind="unit", seed=32)
+    rt = geometry.stage_rot_trans(big.proj_matrix)
+    packed = ops.pack_sources([cu(f) for f in big.features[1:]])
+    gv = torch.randn(6, *big.depth_values.shape, device=DEV)
+    a = ops.costvol_backward_packed(cu(big.features[0]), packed, rt, cu(big.depth_values), gv)
+    b2 = ops.costvol_backward_packed(cu(big.features[0]), packed, rt, cu(big.depth_values), gv)
+    assert torch.equal(a[0], b2[0]) and torch.equal(a[1], b2[1])
+    assert bool(torch.isfinite(a[0]).all()) and bool(torch.isfinite(a[1]).all())
 
 
 # ----------------------------------------------------------------------------- backward (atomic-free)

@@ -22,15 +22,37 @@ int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, i
 
 namespace {
 
+// Tunables (defaults = the values picked by scripts/tune_costvol.py on a B200, see profiles/README.md)
+#ifndef TMVS_TILE_Y
+#define TMVS_TILE_Y 8
+#endif
+#ifndef TMVS_DC
+#define TMVS_DC 8
+#endif
+#ifndef TMVS_MINB8
+#define TMVS_MINB8 2
+#endif
+#ifndef TMVS_MINB4
+#define TMVS_MINB4 4
+#endif
+#ifndef TMVS_MINB2
+#define TMVS_MINB2 5
+#endif
+#ifndef TMVS_UNROLL
+#define TMVS_UNROLL 2
+#endif
+#define TMVS_PRAGMA_(x) _Pragma(#x)
+#define TMVS_PRAGMA(x) TMVS_PRAGMA_(x)
+
 constexpr int kTileX = 32;
-constexpr int kTileY = 8;
-constexpr int kDC = 8;      // depth planes per thread
+constexpr int kTileY = TMVS_TILE_Y;
+constexpr int kDC = TMVS_DC;      // depth planes per thread
 
 // registers -> resident CTAs per SM: the C=32 kernel needs ~128 registers (2 CTAs), the smaller ones fit 3-4
-template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? 2 : (C4T >= 4 ? 3 : 4); };
+template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? TMVS_MINB8 : (C4T >= 4 ? TMVS_MINB4 : TMVS_MINB2); };
 
 template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG>
-__global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value)
+__global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value * (8 / TMVS_TILE_Y))
 costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
                    const float4 *__restrict__ packed, const float *__restrict__ depth,
                    const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
@@ -87,7 +109,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
         const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;
         float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
         const float *dep_p = dep_base;
-#pragma unroll 2
+        TMVS_PRAGMA(unroll TMVS_UNROLL)
         for (int k = 0; k < nd; ++k, dep_p += dep_stride, out_v += HW) {
             const TmvsTaps t = tmvs_taps(ray, rt, __ldg(dep_p), dims);
             float s = 0.0f;
@@ -150,6 +172,13 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
 template <bool PER_PIXEL, typename... Args>
 int launch_c4(int c4, Args... args)
 {
+#ifdef TMVS_FAST_BUILD      // tuning builds: only the three exact kernels
+    switch (c4) {
+    case 2: return launch_mode<2, true, PER_PIXEL>(args...);
+    case 4: return launch_mode<4, true, PER_PIXEL>(args...);
+    default: return launch_mode<8, true, PER_PIXEL>(args...);
+    }
+#else
     switch (c4) {
     case 2: return launch_mode<2, true, PER_PIXEL>(args...);
     case 4: return launch_mode<4, true, PER_PIXEL>(args...);
@@ -159,6 +188,7 @@ int launch_c4(int c4, Args... args)
     if (c4 <= 4) return launch_mode<4, false, PER_PIXEL>(args...);
     if (c4 <= 8) return launch_mode<8, false, PER_PIXEL>(args...);
     return launch_mode<16, false, PER_PIXEL>(args...);
+#endif
 }
 
 __global__ void __launch_bounds__(256)

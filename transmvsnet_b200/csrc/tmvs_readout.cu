@@ -48,6 +48,97 @@ softmax_wta_kernel(const float *__restrict__ logits, const float *__restrict__ d
     conf[(size_t)b * HW + p] = best;
 }
 
+// (p, i) replaces (bp, bi)?  torch.argmax order: larger wins, NaN is the maximum, ties -> smaller index
+__device__ __forceinline__ bool tmvs_takes(float p, int i, float bp, int bi)
+{
+    const bool pn = p != p, bn = bp != bp;
+    if (pn | bn) return pn && (!bn || i < bi);
+    return p > bp || (p == bp && i < bi);
+}
+
+// Small maps (stage 1/2 of the cascade) have too few pixels to fill 148 SMs with one thread per pixel, so the
+// D planes of a pixel are split over SUB threads (different warps: every load is still a coalesced 128-byte
+// row) that combine max / sum / argmax through shared memory.
+template <int PER, int SUB>
+__global__ void __launch_bounds__(32 * SUB)
+softmax_wta_split_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
+                         int64_t *__restrict__ index, float *__restrict__ depth, float *__restrict__ conf, int D,
+                         size_t HW)
+{
+    __shared__ float sh_a[SUB][32];
+    __shared__ float sh_b[SUB][32];
+    __shared__ int sh_i[SUB][32];
+    const int lane = threadIdx.x, sub = threadIdx.y;
+    const size_t p = (size_t)blockIdx.x * 32 + lane;
+    const bool live = p < HW;
+    const int b = blockIdx.y;
+    const float *x = logits + (size_t)b * D * HW + (live ? p : 0);
+    float v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = sub + SUB * k;
+        v[k] = (live && d < D) ? __ldcs(x + (size_t)d * HW) : 0.0f;
+    }
+    // ---- max
+    float m = 0.0f;
+    bool have = false;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = sub + SUB * k;
+        if (d < D && (!have || tmvs_gt(v[k], m))) { m = v[k]; have = true; }
+    }
+    sh_a[sub][lane] = m;
+    sh_i[sub][lane] = have ? 1 : 0;
+    __syncthreads();
+    {
+        float mm = 0.0f;
+        bool h2 = false;
+#pragma unroll
+        for (int j = 0; j < SUB; ++j)
+            if (sh_i[j][lane] && (!h2 || tmvs_gt(sh_a[j][lane], mm))) { mm = sh_a[j][lane]; h2 = true; }
+        m = mm;
+    }
+    // ---- sum of exp
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+        if (sub + SUB * k < D) s += expf(v[k] - m);
+    sh_b[sub][lane] = s;
+    __syncthreads();
+    s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SUB; ++j) s += sh_b[j][lane];
+    const float ls = logf(s);
+    // ---- probabilities + winner
+    float best = 0.0f;
+    int bi = 0x7fffffff;
+    float *pr = (prob && live) ? prob + (size_t)b * D * HW + p : nullptr;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = sub + SUB * k;
+        if (d < D) {
+            const float pv = expf((v[k] - m) - ls);
+            if (pr) __stcs(pr + (size_t)d * HW, pv);
+            if (bi == 0x7fffffff || tmvs_takes(pv, d, best, bi)) { best = pv; bi = d; }
+        }
+    }
+    __syncthreads();                   // sh_a / sh_i are reused
+    sh_a[sub][lane] = best;
+    sh_i[sub][lane] = bi;
+    __syncthreads();
+    if (sub == 0 && live) {
+#pragma unroll
+        for (int j = 1; j < SUB; ++j)
+            if (sh_i[j][lane] != 0x7fffffff && (bi == 0x7fffffff || tmvs_takes(sh_a[j][lane], sh_i[j][lane], best, bi))) {
+                best = sh_a[j][lane];
+                bi = sh_i[j][lane];
+            }
+        index[(size_t)b * HW + p] = bi;
+        depth[(size_t)b * HW + p] = __ldg(dv + ((size_t)b * D + bi) * HW + p);
+        conf[(size_t)b * HW + p] = best;
+    }
+}
+
 // Any D (<= TMVS_MAX_DEPTH): re-reads the logits for each sweep (they sit in L1/L2).
 __global__ void __launch_bounds__(256)
 softmax_wta_generic_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
@@ -148,12 +239,21 @@ extern "C" int tmvs_softmax_wta_fwd(const float *logits, const float *depth_valu
     dim3 grid((unsigned)((HW + 255) / 256), B);
     cudaStream_t st = (cudaStream_t)stream;
 #define TMVS_RO(DT) softmax_wta_kernel<DT><<<grid, 256, 0, st>>>(logits, depth_values, prob, index, depth, conf, D, HW)
+#define TMVS_RO_SPLIT(PER, SUB)                                                                                   \
+    softmax_wta_split_kernel<PER, SUB><<<dim3((unsigned)((HW + 31) / 32), B), dim3(32, SUB), 0, st>>>(            \
+        logits, depth_values, prob, index, depth, conf, D, HW)
+    // one thread per pixel saturates the machine from ~1 M pixels; below that the planes are split over threads
+    const bool small = (size_t)B * HW < ((size_t)1 << 20);
     if (D <= 8) TMVS_RO(8);
+    else if (small && D <= 32 && D > 16) TMVS_RO_SPLIT(4, 8);
+    else if (small && D <= 48 && D > 32) TMVS_RO_SPLIT(6, 8);
+    else if (small && D <= 64 && D > 48) TMVS_RO_SPLIT(8, 8);
     else if (D <= 16) TMVS_RO(16);
     else if (D <= 32) TMVS_RO(32);
     else if (D <= 48) TMVS_RO(48);
     else if (D <= 64) TMVS_RO(64);
     else softmax_wta_generic_kernel<<<grid, 256, 0, st>>>(logits, depth_values, prob, index, depth, conf, D, HW);
+#undef TMVS_RO_SPLIT
 #undef TMVS_RO
     return tmvs_launch_status();
 }

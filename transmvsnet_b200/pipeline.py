@@ -57,6 +57,7 @@ class HostPipeline:
     def __init__(self, device):
         self.device = torch.device(device)
         self._out: Dict[tuple, torch.Tensor] = {}
+        self._copy = None
 
     def _host_out(self, key, like: torch.Tensor) -> torch.Tensor:
         k = (key, tuple(like.shape))
@@ -65,10 +66,28 @@ class HostPipeline:
         return self._out[k]
 
     def process_view(self, host_stages: Sequence[StageInputs]) -> List[Dict[str, torch.Tensor]]:
-        """Returns per stage {"depth", "photo_confidence"} in pinned host memory (valid after a stream sync)."""
+        """Returns per stage {"depth", "photo_confidence"} in pinned host memory (valid after a stream sync).
+
+        All H2D copies are queued on a copy stream up front; each stage's kernels wait only for their own
+        inputs, so stage s+1's inputs cross PCIe while stage s computes, and the D2H of the (small) result maps
+        rides the compute stream behind the kernels that produce them.
+        """
+        compute = torch.cuda.current_stream(self.device)
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(self.device)
+        self._copy.wait_stream(compute)             # buffers of the previous call are free once its kernels ran
+        staged = []
+        with torch.cuda.stream(self._copy):
+            for st in host_stages:
+                dev = stage_to_device(st, self.device)
+                ev = torch.cuda.Event()
+                ev.record(self._copy)
+                staged.append((st, dev, ev))
         results = []
-        for st in host_stages:
-            dev = stage_to_device(st, self.device)
+        for st, dev, ev in staged:
+            compute.wait_event(ev)
+            for t in dev["features"] + [dev["depth_values"], dev["view_weights"], dev["logits"]]:
+                t.record_stream(compute)
             out = run_stage(dev, want_prob=True)
             host = {}
             for key in ("depth", "photo_confidence"):
