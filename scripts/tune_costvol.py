@@ -68,14 +68,16 @@ def main():
     for ty, dc, unroll in itertools.product((8, 4), (8, 16), (1, 2)):
         for mb in ((2, 3, 4), (2, 2, 3), (2, 2, 2), (2, 4, 5)):
             grid.append(dict(TMVS_TILE_Y=ty, TMVS_DC=dc, TMVS_UNROLL=unroll, TMVS_MINB8=mb[0], TMVS_MINB4=mb[1], TMVS_MINB2=mb[2]))
-    if len(sys.argv) > 1:
-        grid = grid[: int(sys.argv[1])]
+    if len(sys.argv) > 1:       # explicit list: '[{"TMVS_DOT_CACHE":0}, ...]' merged over the defaults
+        import json
+        base = dict(TMVS_TILE_Y=8, TMVS_DC=8, TMVS_UNROLL=2, TMVS_MINB8=2, TMVS_MINB4=4, TMVS_MINB2=5, TMVS_DOT_CACHE=1)
+        grid = [{**base, **g} for g in json.loads(sys.argv[1])]
     print("tile_y dc unroll minb(8/4/2)    s1_ms   s2_ms   s3_ms   sum", flush=True)
     for i, defs in enumerate(grid):
         try:
             lib = build_variant(f"v{i}", defs)
             t = time_variant(lib, dev_stages)
-            print(f"{defs['TMVS_TILE_Y']:6d} {defs['TMVS_DC']:2d} {defs['TMVS_UNROLL']:6d} "
+            print(f"cache={defs.get('TMVS_DOT_CACHE', 1)} {defs['TMVS_TILE_Y']:6d} {defs['TMVS_DC']:2d} {defs['TMVS_UNROLL']:6d} "
                   f"{defs['TMVS_MINB8']}/{defs['TMVS_MINB4']}/{defs['TMVS_MINB2']}         "
                   f"{t[0]:7.4f} {t[1]:7.4f} {t[2]:7.4f} {sum(t):7.4f}", flush=True)
         except subprocess.CalledProcessError as e:

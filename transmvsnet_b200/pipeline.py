@@ -58,6 +58,7 @@ class HostPipeline:
         self.device = torch.device(device)
         self._out: Dict[tuple, torch.Tensor] = {}
         self._copy = None
+        self._dev: Dict[tuple, dict] = {}
 
     def _host_out(self, key, like: torch.Tensor) -> torch.Tensor:
         k = (key, tuple(like.shape))
@@ -65,30 +66,48 @@ class HostPipeline:
             self._out[k] = torch.empty(like.shape, dtype=like.dtype).pin_memory()
         return self._out[k]
 
+    def _device_inputs(self, st: StageInputs):
+        """Persistent device buffers for a stage shape (allocated once; no allocator traffic in the steady state)."""
+        key = (st.stage, tuple(st.features[0].shape), len(st.features), tuple(st.depth_values.shape))
+        if key not in self._dev:
+            mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            self._dev[key] = {"features": [mk(f) for f in st.features], "depth_values": mk(st.depth_values),
+                              "view_weights": mk(st.view_weights), "logits": mk(st.logits), "done": None}
+        return self._dev[key]
+
     def process_view(self, host_stages: Sequence[StageInputs]) -> List[Dict[str, torch.Tensor]]:
         """Returns per stage {"depth", "photo_confidence"} in pinned host memory (valid after a stream sync).
 
-        All H2D copies are queued on a copy stream up front; each stage's kernels wait only for their own
-        inputs, so stage s+1's inputs cross PCIe while stage s computes, and the D2H of the (small) result maps
+        H2D copies run on a copy stream into persistent device buffers; each stage's kernels wait only for their
+        own inputs, so stage s+1's inputs cross PCIe while stage s computes.  The D2H of the (small) result maps
         rides the compute stream behind the kernels that produce them.
         """
         compute = torch.cuda.current_stream(self.device)
         if self._copy is None:
             self._copy = torch.cuda.Stream(self.device)
-        self._copy.wait_stream(compute)             # buffers of the previous call are free once its kernels ran
         staged = []
         with torch.cuda.stream(self._copy):
             for st in host_stages:
-                dev = stage_to_device(st, self.device)
+                dev = self._device_inputs(st)
+                if dev["done"] is not None:
+                    self._copy.wait_event(dev["done"])      # the previous view's kernels have consumed these buffers
+                for d, h in zip(dev["features"], st.features):
+                    d.copy_(h, non_blocking=True)
+                dev["depth_values"].copy_(st.depth_values, non_blocking=True)
+                dev["view_weights"].copy_(st.view_weights, non_blocking=True)
+                dev["logits"].copy_(st.logits, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy)
                 staged.append((st, dev, ev))
         results = []
         for st, dev, ev in staged:
             compute.wait_event(ev)
-            for t in dev["features"] + [dev["depth_values"], dev["view_weights"], dev["logits"]]:
-                t.record_stream(compute)
-            out = run_stage(dev, want_prob=True)
+            run_in = {"features": dev["features"], "depth_values": dev["depth_values"],
+                      "view_weights": dev["view_weights"], "logits": dev["logits"],
+                      "rot_trans": stage_rot_trans(st.proj_matrix)}
+            out = run_stage(run_in, want_prob=True)
+            dev["done"] = torch.cuda.Event()
+            dev["done"].record(compute)
             host = {}
             for key in ("depth", "photo_confidence"):
                 buf = self._host_out((st.stage, key), out[key])
