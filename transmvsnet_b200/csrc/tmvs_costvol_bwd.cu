@@ -11,8 +11,9 @@
 //   1. bwd_bbox_kernel: for every (view, reference tile T of 32x8 pixels, depth plane d) the bounding box of
 //      the source pixels T's bilinear footprints touch -- exact, from the same coordinate code as the forward.
 //   2. bwd_src_kernel: one CTA OWNS one 32x8 tile S of grad_src (one thread per source pixel, its C
-//      accumulators in registers).  It scans the boxes, and for every (T, d) that overlaps S, in (T, d)
-//      order:  phase 1 -- thread t recomputes the footprint of reference pixel t of T and registers itself in
+//      accumulators in registers).  It scans the boxes in two levels (8x8-tile groups, then the (T, d) pairs of
+//      the groups that touch S), and for every (T, d) that overlaps S, in (group, T, d) order, up to 4
+//      consecutive planes of a tile per round:  phase 1 -- thread t recomputes the footprint of reference pixel t of T and registers itself in
 //      a shared-memory cell grid indexed by its north-west source pixel (a few rounds of plain stores; which
 //      thread wins a round is irrelevant because phase 2 orders the ids);  phase 2 -- each owner reads the <= 4 cells whose taps
 //      hit its pixel, SORTS the registered thread ids, and accumulates k * ref[:, p] in that order.
@@ -150,16 +151,53 @@ __device__ __forceinline__ void cswap(int &a, int &b)
     a = lo; b = hi;
 }
 
+constexpr int kGroup = 8;            // tiles per side of a scan group (8x8 tiles = 256x64 pixels)
+constexpr int kPlanes = 4;           // depth planes of one reference tile handled per registration round
+constexpr int kSlots2 = 4;           // footprints per cell per plane on the fast path
+
+// Union over ALL planes of the boxes of the 8x8 tiles of a group: the coarse level of the scan.
+__global__ void __launch_bounds__(kThreads)
+bwd_gbox_kernel(const int4 *__restrict__ bbox, int4 *__restrict__ gbox, int D, int n_tx, int n_ty, int n_gx,
+                int n_tiles, int n_groups)
+{
+    __shared__ int red[4][kTY];
+    const int group = blockIdx.x, vb = blockIdx.y;
+    const int gy = group / n_gx, gx = group - gy * n_gx;
+    const int tid = threadIdx.y * kTX + threadIdx.x;
+    int4 r = make_int4(kEmpty, kEmpty, -1, -1);
+    const int4 *boxes = bbox + (size_t)vb * n_tiles * D;
+    for (int j = tid; j < kGroup * kGroup * D; j += kThreads) {
+        const int tl = j / D, d = j - tl * D;
+        const int ty = gy * kGroup + tl / kGroup, tx = gx * kGroup + tl % kGroup;
+        if (tx < n_tx && ty < n_ty) {
+            const int4 bb = __ldg(boxes + (size_t)(ty * n_tx + tx) * D + d);
+            r.x = min(r.x, bb.x); r.y = min(r.y, bb.y); r.z = max(r.z, bb.z); r.w = max(r.w, bb.w);
+        }
+    }
+    r.x = __reduce_min_sync(0xffffffffu, r.x); r.y = __reduce_min_sync(0xffffffffu, r.y);
+    r.z = __reduce_max_sync(0xffffffffu, r.z); r.w = __reduce_max_sync(0xffffffffu, r.w);
+    if (threadIdx.x == 0) { red[0][threadIdx.y] = r.x; red[1][threadIdx.y] = r.y; red[2][threadIdx.y] = r.z; red[3][threadIdx.y] = r.w; }
+    __syncthreads();
+    if (tid == 0) {
+        int4 o = make_int4(kEmpty, kEmpty, -1, -1);
+        for (int w = 0; w < kTY; ++w) { o.x = min(o.x, red[0][w]); o.y = min(o.y, red[1][w]); o.z = max(o.z, red[2][w]); o.w = max(o.w, red[3][w]); }
+        gbox[(size_t)vb * n_groups + group] = o;
+    }
+}
+
 template <int C4T, bool EXACT, bool PER_PIXEL>
 __global__ void __launch_bounds__(kThreads, 2)
 bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth, const float *__restrict__ G,
-               const int4 *__restrict__ bbox, float *__restrict__ grad_src, int b_total, int b_first, int b_chunk,
-               int C, int c4, int D, int H, int W, int n_tx, int n_tiles, const __grid_constant__ TmvsGeom geom)
+               const int4 *__restrict__ bbox, const int4 *__restrict__ gbox, float *__restrict__ grad_src, int b_total,
+               int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_tx, int n_ty, int n_tiles,
+               int n_gx, int n_groups, const __grid_constant__ TmvsGeom geom)
 {
-    __shared__ int cell[kSlots][kCells];
-    __shared__ float krec[4][kThreads];
-    __shared__ int pixrec[kThreads], x0rec[kThreads], y0rec[kThreads];
+    __shared__ int cell[kPlanes][kSlots2][kCells];
+    __shared__ float krec[kPlanes][4][kThreads];
+    __shared__ int x0rec[kPlanes][kThreads], y0rec[kPlanes][kThreads];
+    __shared__ int pixrec[kThreads];
     __shared__ int hits[kThreads];
+    __shared__ int ghits[kThreads];
     __shared__ int wcount[kTY];
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
@@ -176,7 +214,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     const float4 *rimg = refp + (size_t)b * pk.slice;
     const float *gview = G + ((size_t)i * b_total + b) * D * HW;
     const int4 *boxes = bbox + (size_t)blockIdx.z * n_tiles * D;
-    const int n_pairs = n_tiles * D;
+    const int4 *gboxes = gbox + (size_t)blockIdx.z * n_groups;
 
     float4 acc[C4T];
 #pragma unroll
@@ -194,16 +232,13 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
             }
         }
     };
-
-    for (int base = 0; base < n_pairs; base += kThreads) {
-        // ---- which (T, d) pairs of this chunk touch S?  ordered compaction -> deterministic visiting order
-        const int j = base + tid;
-        bool hit = false;
-        if (j < n_pairs) {
-            const int4 bb = __ldg(boxes + j);
-            hit = bb.x <= s_x + kTX - 1 && bb.z >= s_x && bb.y <= s_y + kTY - 1 && bb.w >= s_y;
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    auto overlaps = [&](const int4 &bb) {
+        return bb.x <= s_x + kTX - 1 && bb.z >= s_x && bb.y <= s_y + kTY - 1 && bb.w >= s_y;
+    };
+    // ordered compaction of a per-thread flag into list[]: returns the number of set flags (uniform)
+    auto compact = [&](bool flag, int value, int *list) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        __syncthreads();                       // previous users of wcount / list are done
         if (tx == 0) wcount[ty] = __popc(ballot);
         __syncthreads();
         int prefix = 0, total = 0;
@@ -213,87 +248,138 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
             if (w < ty) prefix += c;
             total += c;
         }
-        if (hit) hits[prefix + __popc(ballot & ((1u << tx) - 1u))] = j;
+        if (flag) list[prefix + __popc(ballot & ((1u << tx) - 1u))] = value;
         __syncthreads();
+        return total;
+    };
 
-        for (int h = 0; h < total; ++h) {
-            const int jj = hits[h];
-            const int tile = jj / D, d = jj - tile * D;
-            const int t_y = tile / n_tx, t_x = tile - t_y * n_tx;
-            // ---- phase 1: thread t = reference pixel t of tile T at plane d
-            const int px = t_x * kTX + tx, py = t_y * kTY + ty;
-            int my_cell = -1;
-            float k00 = 0.f, k01 = 0.f, k10 = 0.f, k11 = 0.f;
-            int x0 = kEmpty, y0 = kEmpty;
-            if (px < W && py < H) {
-                const size_t pix = (size_t)py * W + px;
-                const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
-                const TmvsRay ray = tmvs_ray(rt, (float)px, (float)py);
-                const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
-                const int cx = t.x0 - s_x + 1, cy = t.y0 - s_y + 1;
-                if (t.any && cx >= 0 && cx < kCellW && cy >= 0 && cy < kCellH) {
-                    const float gw = __ldg(gview + (size_t)d * HW + pix) * inv_c;
-                    k00 = t.ok00 ? gw * t.w00 : 0.0f; k01 = t.ok01 ? gw * t.w01 : 0.0f;
-                    k10 = t.ok10 ? gw * t.w10 : 0.0f; k11 = t.ok11 ? gw * t.w11 : 0.0f;
-                    my_cell = cy * kCellW + cx;
-                    x0 = t.x0; y0 = t.y0;
+    // ---- level 1: groups of 8x8 reference tiles whose all-plane box touches S (visited in group order)
+    for (int gbase = 0; gbase < n_groups; gbase += kThreads) {
+        const int gj = gbase + tid;
+        const bool ghit = gj < n_groups && overlaps(__ldg(gboxes + gj));
+        const int n_gh = compact(ghit, gj, ghits);
+        for (int gh = 0; gh < n_gh; ++gh) {
+            const int group = ghits[gh];
+            const int g_y = group / n_gx, g_x = group - g_y * n_gx;
+            // ---- level 2: the (tile, plane) pairs of this group, tile-major / plane-minor
+            const int n_pairs = kGroup * kGroup * D;
+            for (int base = 0; base < n_pairs; base += kThreads) {
+                const int j = base + tid;
+                bool hit = false;
+                int code = 0;
+                if (j < n_pairs) {
+                    const int tl = j / D, d = j - tl * D;
+                    const int t_y = g_y * kGroup + tl / kGroup, t_x = g_x * kGroup + tl % kGroup;
+                    if (t_x < n_tx && t_y < n_ty) {
+                        const int tile = t_y * n_tx + t_x;
+                        hit = overlaps(__ldg(boxes + (size_t)tile * D + d));
+                        code = tile * D + d;
+                    }
                 }
-            }
-            krec[0][tid] = k00; krec[1][tid] = k01; krec[2][tid] = k10; krec[3][tid] = k11;
-            pixrec[tid] = tmvs_pk_off(pk, min(px, W - 1), min(py, H - 1) * pk.row);   // packed word of ref pixel p
-            x0rec[tid] = x0; y0rec[tid] = y0;
-            for (int c = tid; c < kSlots * kCells; c += kThreads) (&cell[0][0])[c] = kEmpty;
-            __syncthreads();
-            // registration rounds: plain stores; one registrant per cell per round survives, the rest retry.
-            // WHICH one survives does not matter: phase 2 sorts the ids of a cell before summing.
-            bool pending = my_cell >= 0;
-            int left = 0;
-#pragma unroll 1
-            for (int r = 0; r < kSlots; ++r) {
-                if (pending) cell[r][my_cell] = tid;
-                __syncthreads();
-                if (pending && cell[r][my_cell] == tid) pending = false;
-                left = __syncthreads_or(pending);
-                if (!left) break;
-            }
-            // ---- phase 2: the owner of source pixel q gathers the taps that land on it
-            if (q_valid) {
-                if (!left) {
-                    const int c00 = (ty + 1) * kCellW + (tx + 1), c01 = (ty + 1) * kCellW + tx;
-                    const int c10 = ty * kCellW + (tx + 1), c11 = ty * kCellW + tx;
-                    const int cls_cell[4] = {c00, c01, c10, c11};
+                const int total = compact(hit, code, hits);
+
+                int h = 0;
+                while (h < total) {
+                    // a run of up to kPlanes consecutive planes of ONE reference tile
+                    const int jj = hits[h];
+                    const int tile = jj / D, d_first = jj - tile * D;
+                    int run = 1;
+                    while (run < kPlanes && h + run < total && hits[h + run] == jj + run && d_first + run < D) ++run;
+                    h += run;
+                    const int t_y = tile / n_tx, t_x = tile - t_y * n_tx;
+                    // ---- phase 1: thread t = reference pixel t of tile T, for each plane of the run
+                    const int px = t_x * kTX + tx, py = t_y * kTY + ty;
+                    const bool p_valid = px < W && py < H;
+                    int my_cell[kPlanes];
+                    TmvsRay ray;
+                    if (p_valid) ray = tmvs_ray(rt, (float)px, (float)py);
+                    pixrec[tid] = tmvs_pk_off(pk, min(px, W - 1), min(py, H - 1) * pk.row);   // packed word of ref pixel p
 #pragma unroll
-                    for (int cls = 0; cls < 4; ++cls) {
-                        int i0 = cell[0][cls_cell[cls]], i1 = cell[1][cls_cell[cls]];
-                        int i2 = cell[2][cls_cell[cls]], i3 = cell[3][cls_cell[cls]];
-                        if (i1 != kEmpty) {           // several footprints share the cell: fix the order
-                            cswap(i0, i1); cswap(i2, i3); cswap(i0, i2); cswap(i1, i3); cswap(i1, i2);
+                    for (int pl = 0; pl < kPlanes; ++pl) {
+                        my_cell[pl] = -1;
+                        float k00 = 0.f, k01 = 0.f, k10 = 0.f, k11 = 0.f;
+                        int x0 = kEmpty, y0 = kEmpty;
+                        if (pl < run && p_valid) {
+                            const int d = d_first + pl;
+                            const size_t pix = (size_t)py * W + px;
+                            const float dep = PER_PIXEL ? __ldg(depth + ((size_t)b * D + d) * HW + pix) : __ldg(depth + (size_t)b * D + d);
+                            const TmvsTaps t = tmvs_taps(ray, rt, dep, dims);
+                            const int cx = t.x0 - s_x + 1, cy = t.y0 - s_y + 1;
+                            if (t.any && cx >= 0 && cx < kCellW && cy >= 0 && cy < kCellH) {
+                                const float gw = __ldg(gview + (size_t)d * HW + pix) * inv_c;
+                                k00 = t.ok00 ? gw * t.w00 : 0.0f; k01 = t.ok01 ? gw * t.w01 : 0.0f;
+                                k10 = t.ok10 ? gw * t.w10 : 0.0f; k11 = t.ok11 ? gw * t.w11 : 0.0f;
+                                my_cell[pl] = cy * kCellW + cx;
+                                x0 = t.x0; y0 = t.y0;
+                            }
                         }
-                        const int ids[4] = {i0, i1, i2, i3};
+                        if (pl < run) {
+                            krec[pl][0][tid] = k00; krec[pl][1][tid] = k01; krec[pl][2][tid] = k10; krec[pl][3][tid] = k11;
+                            x0rec[pl][tid] = x0; y0rec[pl][tid] = y0;
+                        }
+                    }
+                    for (int c = tid; c < run * kSlots2 * kCells; c += kThreads) (&cell[0][0][0])[c] = kEmpty;
+                    __syncthreads();
+                    // registration rounds: plain stores; one registrant per cell per round survives, the rest
+                    // retry in the next slot.  WHICH one survives does not matter: phase 2 orders the ids of a cell.
+                    unsigned pend = 0;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (ids[u] != kEmpty) {
-                                const float k = krec[cls][ids[u]];
-                                if (k != 0.0f) accumulate(k, pixrec[ids[u]]);
+                    for (int pl = 0; pl < kPlanes; ++pl)
+                        if (my_cell[pl] >= 0) pend |= 1u << pl;
+                    int left = 0;
+#pragma unroll 1
+                    for (int r = 0; r < kSlots2; ++r) {
+#pragma unroll
+                        for (int pl = 0; pl < kPlanes; ++pl)
+                            if (pend & (1u << pl)) cell[pl][r][my_cell[pl]] = tid;
+                        __syncthreads();
+#pragma unroll
+                        for (int pl = 0; pl < kPlanes; ++pl)
+                            if ((pend & (1u << pl)) && cell[pl][r][my_cell[pl]] == tid) pend &= ~(1u << pl);
+                        left = __syncthreads_or(pend != 0);
+                        if (!left) break;
+                    }
+                    // ---- phase 2: the owner of source pixel q gathers the taps that land on it, plane by plane
+                    if (q_valid) {
+                        const int cls_cell[4] = {(ty + 1) * kCellW + (tx + 1), (ty + 1) * kCellW + tx,
+                                                 ty * kCellW + (tx + 1), ty * kCellW + tx};
+                        for (int pl = 0; pl < run; ++pl) {
+                            if (!left) {
+#pragma unroll
+                                for (int cls = 0; cls < 4; ++cls) {
+                                    int i0 = cell[pl][0][cls_cell[cls]], i1 = cell[pl][1][cls_cell[cls]];
+                                    int i2 = cell[pl][2][cls_cell[cls]], i3 = cell[pl][3][cls_cell[cls]];
+                                    if (i1 != kEmpty) {           // several footprints share the cell: fix the order
+                                        cswap(i0, i1); cswap(i2, i3); cswap(i0, i2); cswap(i1, i3); cswap(i1, i2);
+                                    }
+                                    const int ids[4] = {i0, i1, i2, i3};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        if (ids[u] != kEmpty) {
+                                            const float k = krec[pl][cls][ids[u]];
+                                            if (k != 0.0f) accumulate(k, pixrec[ids[u]]);
+                                        }
+                                    }
+                                }
+                            } else {
+                                // exhaustive, still ordered (class, then reference-pixel id)
+#pragma unroll 1
+                                for (int cls = 0; cls < 4; ++cls) {
+                                    const int want_x = qx - (cls & 1), want_y = qy - (cls >> 1);
+#pragma unroll 1
+                                    for (int t2 = 0; t2 < kThreads; ++t2) {
+                                        if (x0rec[pl][t2] == want_x && y0rec[pl][t2] == want_y) {
+                                            const float k = krec[pl][cls][t2];
+                                            if (k != 0.0f) accumulate(k, pixrec[t2]);
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
-                } else {
-                    // more than kSlots footprints on one cell (strong minification): exhaustive, still ordered
-#pragma unroll 1
-                    for (int cls = 0; cls < 4; ++cls) {
-                        const int want_x = qx - (cls & 1), want_y = qy - (cls >> 1);
-#pragma unroll 1
-                        for (int t2 = 0; t2 < kThreads; ++t2) {
-                            if (x0rec[t2] == want_x && y0rec[t2] == want_y) {
-                                const float k = krec[cls][t2];
-                                if (k != 0.0f) accumulate(k, pixrec[t2]);
-                            }
-                        }
-                    }
+                    __syncthreads();
                 }
             }
-            __syncthreads();
         }
     }
     if (q_valid) {
@@ -311,7 +397,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
 inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct BwdWorkspace {
-    size_t ref_packed, partial, bbox, total;
+    size_t ref_packed, partial, bbox, gbox, total;
 };
 
 inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
@@ -322,17 +408,21 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.ref_packed = 0;
     ws.partial = align256((size_t)B * tmvs_packed_layout((C + 3) / 4, H, W).slice * 16);
     ws.bbox = ws.partial + align256((size_t)n_src * B * C * HW * 4);
-    ws.total = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
+    ws.gbox = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
+    const size_t n_groups = (size_t)(((W + kTX - 1) / kTX + kGroup - 1) / kGroup) * (((H + kTY - 1) / kTY + kGroup - 1) / kGroup);
+    ws.total = ws.gbox + align256((size_t)n_src * B * n_groups * 16);
     return ws;
 }
 
 template <bool PER_PIXEL>
 int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st, const float4 *packed,
-               const float4 *refp, const float *depth, const float *G, float *partial, int4 *bbox, float *grad_src,
-               int b_total, int b_first, int b_chunk, int C, int D, int H, int W, int n_tx, int n_tiles,
-               const TmvsGeom &geom)
+               const float4 *refp, const float *depth, const float *G, float *partial, int4 *bbox, int4 *gbox,
+               float *grad_src, int b_total, int b_first, int b_chunk, int C, int D, int H, int W, int n_tx,
+               int n_tiles, const TmvsGeom &geom)
 {
     dim3 block(kTX, kTY);
+    const int n_ty = n_tiles / n_tx;
+    const int n_gx = (n_tx + kGroup - 1) / kGroup, n_gy = (n_ty + kGroup - 1) / kGroup, n_groups = n_gx * n_gy;
 #define TMVS_BWD(C4T, EX)                                                                                          \
     do {                                                                                                           \
         if (want_ref)                                                                                              \
@@ -341,9 +431,11 @@ int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st,
         if (want_src) {                                                                                            \
             bwd_bbox_kernel<PER_PIXEL><<<grid, block, 0, st>>>(depth, bbox, b_first, b_chunk, D, H, W, n_tx,       \
                                                                n_tiles, geom);                                     \
-            bwd_src_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(refp, depth, G, bbox, grad_src, b_total,    \
-                                                                       b_first, b_chunk, C, c4, D, H, W, n_tx,     \
-                                                                       n_tiles, geom);                             \
+            bwd_gbox_kernel<<<dim3(n_groups, grid.z), block, 0, st>>>(bbox, gbox, D, n_tx, n_ty, n_gx, n_tiles,    \
+                                                                      n_groups);                                   \
+            bwd_src_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(refp, depth, G, bbox, gbox, grad_src,       \
+                                                                       b_total, b_first, b_chunk, C, c4, D, H, W,  \
+                                                                       n_tx, n_ty, n_tiles, n_gx, n_groups, geom); \
         }                                                                                                          \
     } while (0)
     if (c4 == 2) TMVS_BWD(2, true);
@@ -382,6 +474,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     float *refp = (float *)(wsp + ws.ref_packed);
     float *partial = (float *)(wsp + ws.partial);
     int4 *bbox = (int4 *)(wsp + ws.bbox);
+    int4 *gbox = (int4 *)(wsp + ws.gbox);
     const int c4 = (C + 3) / 4;
     const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY, n_tiles = n_tx * n_ty;
     const size_t HW = (size_t)H * W;
@@ -403,11 +496,11 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         int rc;
         if (per_pixel)
             rc = launch_bwd<true>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
-                                  (const float4 *)refp, depth, grad_views, partial, bbox, grad_src, B, b0, bc, C, D, H,
+                                  (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
                                   W, n_tx, n_tiles, geom);
         else
             rc = launch_bwd<false>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
-                                   (const float4 *)refp, depth, grad_views, partial, bbox, grad_src, B, b0, bc, C, D, H,
+                                   (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
                                    W, n_tx, n_tiles, geom);
         if (rc != TMVS_OK) return rc;
     }
