@@ -95,6 +95,29 @@ int tmvs_aggregate_fwd(const float *sim_views, const float *view_weights, float 
                        int B, int D, int H, int W, int n_src, tmvs_stream_t stream);
 
 /*
+ * SURVEY.md 8(f) N1 -- depth hypotheses of a cascade stage in one kernel, at the stage resolution:
+ * replaces models/TransMVSNet.py:174-190 (bilinear upsample of the previous depth to the image size +
+ * get_depth_samples, models/module.py:606-634) and :202-204 (trilinear resample to [D, h, w]) without
+ * materialising the [B, D, Himg, Wimg] volume.
+ *   prev_depth   [B][hp][wp] previous-stage depth (prev_planes = 0), or [B][n_planes] depth_values (prev_planes = n)
+ *   out          [B][D][h][w], h = Himg / scale, w = Wimg / scale, scale in {1, 2, 4}
+ *   interval     depth_inteval_pixel of the stage (ratio * depth_interval), used when prev_planes = 0
+ */
+int tmvs_depth_hypotheses_fwd(const float *prev_depth, int prev_planes, int hp, int wp, float interval, float *out,
+                              int B, int D, int h, int w, int scale, tmvs_stream_t stream);
+
+/*
+ * SURVEY.md 8(f) N2 -- eval-mode PixelwiseNet folded into the aggregation (models/TransMVSNet.py:10-30, 82-93):
+ * for every source view   w_i = max_d sigmoid(MLP(sim_i[d])),  MLP = 1->16->8->1 per-voxel (1x1x1 Conv3d with the
+ * BatchNorm3d running statistics folded in, ReLU),  then  agg = sum_i sim_i*w_i / (1e-5 + sum_i w_i).
+ * mlp = HOST array of TMVS_PWN_PARAMS floats: w0[16], b0[16], w1[8][16], b1[8], w2[8], b2.
+ * Outputs: view_weights [B][Nsrc][H][W] and agg [B][D][H][W].  Inference only (training needs batch statistics).
+ */
+#define TMVS_PWN_PARAMS 177
+int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float *view_weights, float *agg,
+                                 int B, int D, int H, int W, int n_src, tmvs_stream_t stream);
+
+/*
  * Backward of the cost volume wrt the features (autograd of models/module.py:318-320 and
  * models/TransMVSNet.py:80).  grad_views = dL/d sim_i [Nsrc][B][D][H][W].
  *   grad_ref  [B][C][H][W]            (contiguous NCHW, overwritten)

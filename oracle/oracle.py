@@ -122,3 +122,23 @@ def depth_regression(p, depth_values) -> np.ndarray:
     lib().tmvs_oracle_depth_regression(_f(p), _f(depth_values), int(depth_values.ndim == 4), _f(dep),
                                        b, d, h, w)
     return dep
+
+
+def pixelwise_weights(sim_views, state) -> np.ndarray:
+    """Eval-mode PixelwiseNet of every view.  sim_views [N,B,D,H,W]; state = the reference module's state_dict
+    as numpy arrays (keys conv0.conv.weight, conv0.bn.weight, ...) -> view_weights [B,N,H,W]."""
+    sim_views = _c(sim_views)
+    n, b, d, h, w = sim_views.shape
+    g = lambda k: _c(np.asarray(state[k]).reshape(-1))
+    bn = lambda pre: _c(np.stack([np.asarray(state[pre + s]).reshape(-1) for s in
+                                  (".weight", ".bias", ".running_mean", ".running_var")]))
+    w0, w1, w2 = g("conv0.conv.weight"), g("conv1.conv.weight"), g("conv2.weight")
+    bn0, bn1 = bn("conv0.bn"), bn("conv1.bn")
+    b2 = float(np.asarray(state["conv2.bias"]).reshape(-1)[0])
+    out = np.empty((b, n, h, w), np.float32)
+    for i in range(n):
+        wi = np.empty((b, h, w), np.float32)
+        lib().tmvs_oracle_pixelwise_weight(_f(np.ascontiguousarray(sim_views[i])), _f(w0), _f(bn0), _f(w1), _f(bn1),
+                                           _f(w2), ctypes.c_float(b2), ctypes.c_float(1e-5), _f(wi), b, d, h, w)
+        out[:, i] = wi
+    return out

@@ -336,3 +336,43 @@ void tmvs_oracle_depth_regression(const float *p, const float *depth_values, int
             depth[(size_t)b * HW + q] = acc;
         }
 }
+
+/* ------------------------------------------------------------------------- */
+/* PixelwiseNet in eval mode: models/TransMVSNet.py:10-30 with ConvBnReLU3D    */
+/* (models/module.py:214-221): 1x1x1 Conv3d (no bias) -> BatchNorm3d (running   */
+/* statistics) -> ReLU, twice (1->16->8), then Conv3d 8->1 with bias, Sigmoid,  */
+/* max over D.  NOT folded: conv and batch-norm are applied one after the other */
+/* as the reference does.  sim [B,D,H,W] of ONE view -> weight [B,H,W].         */
+/* bn arrays are [4][n]: gamma, beta, running_mean, running_var.                */
+/* ------------------------------------------------------------------------- */
+void tmvs_oracle_pixelwise_weight(const float *sim, const float *w0, const float *bn0, const float *w1,
+                                  const float *bn1, const float *w2, float b2, float eps, float *weight,
+                                  int B, int D, int H, int W)
+{
+    const size_t HW = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (size_t p = 0; p < HW; ++p) {
+            float best = -INFINITY;
+            for (int d = 0; d < D; ++d) {
+                float x = sim[((size_t)b * D + d) * HW + p];
+                float h0[16], h1[8];
+                for (int c = 0; c < 16; ++c) {
+                    float y = w0[c] * x;
+                    y = (y - bn0[2 * 16 + c]) / sqrtf(bn0[3 * 16 + c] + eps) * bn0[c] + bn0[16 + c];
+                    h0[c] = y > 0.0f ? y : 0.0f;
+                }
+                for (int j = 0; j < 8; ++j) {
+                    float y = 0.0f;
+                    for (int c = 0; c < 16; ++c) y += w1[j * 16 + c] * h0[c];
+                    y = (y - bn1[2 * 8 + j]) / sqrtf(bn1[3 * 8 + j] + eps) * bn1[j] + bn1[8 + j];
+                    h1[j] = y > 0.0f ? y : 0.0f;
+                }
+                float o = b2;
+                for (int j = 0; j < 8; ++j) o += w2[j] * h1[j];
+                float sg = 1.0f / (1.0f + expf(-o));
+                if (sg > best) best = sg;
+            }
+            weight[(size_t)b * HW + p] = best;
+        }
+}

@@ -111,3 +111,25 @@ def hot_path(stage_inputs) -> dict:
                          stage_inputs.view_weights)
     prob, idx, depth, conf = read_out(stage_inputs.logits, stage_inputs.depth_values)
     return {"similarity": agg, "prob_volume": prob, "index": idx, "depth": depth, "photo_confidence": conf}
+
+
+def depth_hypotheses(cur_depth: torch.Tensor, ndepth: int, interval_pixel: float, image_hw, stage_scale: int) -> torch.Tensor:
+    """Stage hypotheses as the reference builds them (models/TransMVSNet.py:174-190, 202-204 with
+    models/module.py:606-634), restated with the same ATen ops: cur_depth is depth_values [B,192] (stage 1)
+    or the previous stage's depth [B,hp,wp]."""
+    h_img, w_img = image_hw
+    b = cur_depth.shape[0]
+    steps = torch.arange(0, ndepth, dtype=cur_depth.dtype, device=cur_depth.device)
+    if cur_depth.dim() == 2:
+        lo, hi = cur_depth[:, 0], cur_depth[:, -1]
+        step = (hi - lo) / (ndepth - 1)
+        vol = lo[:, None] + steps[None] * step[:, None]
+        vol = vol[:, :, None, None].repeat(1, 1, h_img, w_img)
+    else:
+        up = F.interpolate(cur_depth.unsqueeze(1), [h_img, w_img], mode="bilinear", align_corners=False).squeeze(1)
+        lo = up - ndepth / 2 * interval_pixel
+        hi = up + ndepth / 2 * interval_pixel
+        step = (hi - lo) / (ndepth - 1)
+        vol = lo.unsqueeze(1) + steps.reshape(1, -1, 1, 1) * step.unsqueeze(1)
+    return F.interpolate(vol.unsqueeze(1), [ndepth, h_img // stage_scale, w_img // stage_scale], mode="trilinear",
+                         align_corners=False).squeeze(1)

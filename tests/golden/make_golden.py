@@ -166,7 +166,35 @@ def regression_case():
          depth_4d=torch.sum(p * dv4, 1), depth_2d=torch.sum(p * dv2.view(2, 9, 1, 1), 1))
 
 
+def hypotheses_case():
+    """Stage hypotheses through the reference's own ops: F.interpolate (bilinear) -> get_depth_samples
+    (models/module.py:606-634) -> F.interpolate (trilinear), exactly as models/TransMVSNet.py:174-190, 202-204."""
+    import torch.nn.functional as F
+    from models.module import get_depth_samples
+    g = torch.Generator().manual_seed(51)
+    b, h_img, w_img = 2, 48, 64
+    dv = (425.0 + 2.5 * torch.arange(192, dtype=torch.float32))[None].repeat(b, 1)
+    dv[1] += 7.0
+    interval = float((dv[0, -1] - dv[0, 0]) / 192)
+    arrays = {"depth_values": dv, "image_hw": np.array([h_img, w_img]), "depth_interval": np.float32(interval)}
+    prev = {2: 500 + 300 * torch.rand(b, h_img // 4, w_img // 4, generator=g),
+            3: 500 + 300 * torch.rand(b, h_img // 2, w_img // 2, generator=g)}
+    for stage, (nd, ratio, scale) in enumerate(((48, 4.0, 4), (32, 1.0, 2), (8, 0.5, 1)), start=1):
+        if stage == 1:
+            cur = dv
+        else:
+            cur = F.interpolate(prev[stage].unsqueeze(1), [h_img, w_img], mode="bilinear", align_corners=False).squeeze(1)
+            arrays[f"prev{stage}"] = prev[stage]
+        samples = get_depth_samples(cur_depth=cur, ndepth=nd, depth_inteval_pixel=ratio * interval, dtype=torch.float32,
+                                    device=torch.device("cpu"), shape=[b, h_img, w_img])
+        out = F.interpolate(samples.unsqueeze(1), [nd, h_img // scale, w_img // scale], mode="trilinear",
+                            align_corners=False).squeeze(1)
+        arrays[f"hyp{stage}"] = out
+    save("hypotheses", **arrays)
+
+
 if __name__ == "__main__":
+    hypotheses_case()
     warp_cases()
     depthnet_cases()
     readout_cases()

@@ -393,6 +393,53 @@ def test_depthnet_forward_given_weights(name):
     assert np.abs(out["photo_confidence"].cpu().numpy() - g["photo_confidence"]).max() <= 5e-5
 
 
+def test_depth_hypotheses_kernel():
+    """stage hypotheses in one kernel against the reference's interpolate -> get_depth_samples ->
+    interpolate chain (golden), and against the torch port at the DTU image size (stage 2)."""
+    from oracle import torch_port
+    g = golden("hypotheses")
+    hw = tuple(int(v) for v in g["image_hw"])
+    iv = float(g["depth_interval"])
+    rng = float(g["depth_values"].max() - g["depth_values"].min())
+    for stage, (nd, ratio, scale) in enumerate(((48, 4.0, 4), (32, 1.0, 2), (8, 0.5, 1)), start=1):
+        cur = cu(g["depth_values"] if stage == 1 else g[f"prev{stage}"])
+        out = tm.depth_hypotheses(cur, nd, ratio * iv, hw, scale)
+        assert tuple(out.shape) == g[f"hyp{stage}"].shape
+        assert np.abs(out.cpu().numpy() - g[f"hyp{stage}"]).max() <= 1e-6 * rng       # a few ulp of ~900 mm
+    prev = 500 + 300 * torch.rand(1, 288, 400, generator=torch.Generator().manual_seed(2))
+    want = torch_port.depth_hypotheses(prev, 32, 2.4869792, (1152, 1600), 2)
+    got = tm.depth_hypotheses(cu(prev), 32, 2.4869792, (1152, 1600), 2)
+    assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 1e-6 * rng
+
+
+def test_pixelwise_aggregate_folded_kernel():
+    """eval-mode PixelwiseNet folded into the aggregation kernel, against the reference's
+    view weights / aggregated similarity (golden) and the unfused C oracle."""
+    g = golden("depthnet_s1_learned")
+    pwn = tm.PixelwiseNet().eval()
+    pwn.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("pwn.")})
+    feats = [cu(f) for f in g["features"]]
+    _, views = tm.cost_volume(feats[0], feats[1:], g["rot_trans"], cu(g["depth_values"]), None, want_views=True)
+    vw, agg = tm.pixelwise_aggregate(views, tm.fold_pixelwise_net(pwn))
+    assert np.abs(vw.cpu().numpy() - g["view_weights"]).max() <= 1e-5
+    assert_costvol_close(agg.cpu().numpy(), g["similarity"][:, 0], "folded PixelwiseNet aggregate")
+    o_vw = oracle.pixelwise_weights(views.cpu().numpy(), {k[4:]: v for k, v in g.items() if k.startswith("pwn.")})
+    assert np.abs(vw.cpu().numpy() - o_vw).max() <= 1e-5
+    # non-trivial batch-norm statistics (a trained net has them): fold vs the PyTorch module itself
+    torch.manual_seed(3)
+    net = tm.PixelwiseNet()
+    for bn in (net.conv0.bn, net.conv1.bn):
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.data.normal_(1, 0.2)
+        bn.bias.data.normal_(0, 0.2)
+    net = net.eval().to(DEV)
+    with torch.no_grad():
+        want = torch.cat([net(views[i].unsqueeze(1)) for i in range(views.shape[0])], 1)
+    got, _ = tm.pixelwise_aggregate(views, tm.fold_pixelwise_net(net))
+    assert float((got - want).abs().max()) <= 1e-5
+
+
 def test_depthnet_forward_learned_weights():
     g = golden("depthnet_s1_learned")
     net = tm.DepthNet().eval()

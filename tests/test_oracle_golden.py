@@ -103,6 +103,31 @@ def test_c_oracle_stage1_learned_weights():
     assert_costvol_close(oracle.aggregate_fwd(views, vw), g["similarity"][:, 0], "stage-1 aggregate")
 
 
+def test_c_oracle_pixelwise_net_matches_reference():
+    """The plain-C PixelwiseNet (conv, then batch-norm, unfused) against the reference module's own output."""
+    g = golden("depthnet_s1_learned")
+    feats = g["features"]
+    views, _ = oracle.costvol_fwd(feats[0], feats[1:], g["rot_trans"], g["depth_values"], None)
+    state = {k[4:]: v for k, v in g.items() if k.startswith("pwn.")}
+    vw = oracle.pixelwise_weights(views, state)
+    assert np.abs(vw - g["view_weights"]).max() <= 1e-5
+
+
+def test_folded_pixelwise_params_shape():
+    from transmvsnet_b200 import fold_pixelwise_net, PixelwiseNet
+    assert fold_pixelwise_net(PixelwiseNet().eval()).shape == (177,)
+
+
+def test_torch_port_depth_hypotheses_bit_exact():
+    g = golden("hypotheses")
+    hw = tuple(int(v) for v in g["image_hw"])
+    iv = float(g["depth_interval"])
+    for stage, (nd, ratio, scale) in enumerate(((48, 4.0, 4), (32, 1.0, 2), (8, 0.5, 1)), start=1):
+        cur = torch.tensor(g["depth_values"] if stage == 1 else g[f"prev{stage}"])
+        out = torch_port.depth_hypotheses(cur, nd, ratio * iv, hw, scale).numpy()
+        assert np.array_equal(out, g[f"hyp{stage}"]), stage
+
+
 def test_wta_ties_first_maximal():
     g = golden("wta_ties")
     idx, dep = oracle.depth_wta(g["p"], g["depth_values"])

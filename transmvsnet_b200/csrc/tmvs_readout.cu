@@ -223,6 +223,65 @@ depth_regression_bwd_kernel(const float *__restrict__ gdepth, const float *__res
     }
 }
 
+// ATen upsample (align_corners=False): source index of destination index i for ratio r = in/out
+__device__ __forceinline__ float area_src(int i, float r)
+{
+    const float s = r * ((float)i + 0.5f) - 0.5f;
+    return s < 0.0f ? 0.0f : s;
+}
+
+// value of the bilinearly upsampled previous depth at image pixel (iy, ix)   (TransMVSNet.py:175-178)
+__device__ __forceinline__ float upsampled_prev(const float *__restrict__ prev, int hp, int wp, float ry, float rx,
+                                                int iy, int ix)
+{
+    const float sy = area_src(iy, ry), sx = area_src(ix, rx);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < hp - 1 ? 1 : 0), x1 = x0 + (x0 < wp - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+    return ly0 * (lx0 * __ldg(prev + (size_t)y0 * wp + x0) + lx1 * __ldg(prev + (size_t)y0 * wp + x1)) +
+           ly1 * (lx0 * __ldg(prev + (size_t)y1 * wp + x0) + lx1 * __ldg(prev + (size_t)y1 * wp + x1));
+}
+
+__global__ void __launch_bounds__(256)
+depth_hypotheses_kernel(const float *__restrict__ prev, int prev_planes, int hp, int wp, float interval,
+                        float *__restrict__ out, int D, int h, int w, int scale)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int b = blockIdx.z;
+    const size_t hw = (size_t)h * w;
+    float *o = out + (size_t)b * D * hw + (size_t)y * w + x;
+    if (prev_planes > 0) {
+        // 2-D branch of get_depth_samples (module.py:616-623): the global range cut into D planes
+        const float lo = __ldg(prev + (size_t)b * prev_planes), hi = __ldg(prev + (size_t)b * prev_planes + prev_planes - 1);
+        const float step = (hi - lo) / (float)(D - 1);
+        for (int d = 0; d < D; ++d) o[(size_t)d * hw] = lo + (float)d * step;
+        return;
+    }
+    // 3-D branch (module.py:624-632) at the image pixels the trilinear resample (TransMVSNet.py:202-204,
+    // align_corners=False) blends: for scale 2 / 4 the two centre pixels of each axis with weight 1/2 each
+    const int himg = h * scale, wimg = w * scale;
+    const float ry = (float)hp / (float)himg, rx = (float)wp / (float)wimg;
+    const float *pv = prev + (size_t)b * hp * wp;
+    const int off = scale == 1 ? 0 : scale / 2 - 1;           // first of the two blended pixels
+    const int n = scale == 1 ? 1 : 2;
+    const float half_span = (float)D / 2.0f * interval;
+    for (int d = 0; d < D; ++d) {
+        float acc_y[2] = {0.0f, 0.0f};
+        for (int j = 0; j < n; ++j) {
+            float vx[2] = {0.0f, 0.0f};
+            for (int i = 0; i < n; ++i) {
+                const float up = upsampled_prev(pv, hp, wp, ry, rx, y * scale + off + j, x * scale + off + i);
+                const float cur_min = up - half_span, cur_max = up + half_span;
+                const float step = (cur_max - cur_min) / (float)(D - 1);
+                vx[i] = cur_min + (float)d * step;
+            }
+            acc_y[j] = n == 1 ? vx[0] : 0.5f * vx[0] + 0.5f * vx[1];
+        }
+        o[(size_t)d * hw] = n == 1 ? acc_y[0] : 0.5f * acc_y[0] + 0.5f * acc_y[1];
+    }
+}
+
 inline bool bad_dims(int B, int D, int H, int W)
 {
     return B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535 || D > TMVS_MAX_DEPTH;
@@ -294,6 +353,19 @@ extern "C" int tmvs_depth_regression_bwd(const float *grad_depth, const float *d
         depth_regression_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
     else
         depth_regression_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_depth_hypotheses_fwd(const float *prev_depth, int prev_planes, int hp, int wp, float interval,
+                                         float *out, int B, int D, int h, int w, int scale, tmvs_stream_t stream)
+{
+    if (!prev_depth || !out) return TMVS_E_NULL;
+    if (bad_dims(B, D, h, w) || D < 2) return TMVS_E_SHAPE;
+    if (scale != 1 && scale != 2 && scale != 4) return TMVS_E_UNSUPPORTED;
+    if (prev_planes < 0 || (prev_planes == 0 && (hp <= 0 || wp <= 0)) || prev_planes == 1) return TMVS_E_SHAPE;
+    dim3 grid((w + 31) / 32, (h + 7) / 8, B);
+    depth_hypotheses_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(prev_depth, prev_planes, hp, wp, interval,
+                                                                           out, D, h, w, scale);
     return tmvs_launch_status();
 }
 

@@ -69,9 +69,14 @@ class DepthNet(nn.Module):
         learned = view_weights is None
         if learned:
             _, sim_views = ops.cost_volume(ref_feature, src_features, rot_trans, depth_values, None, True)
-            weights = [self.pixel_wise_net(sim_views[i].unsqueeze(1)) for i in range(sim_views.shape[0])]
-            view_weights = torch.cat(weights, dim=1)                       # [B,Nsrc,H,W]
-            similarity = ops.aggregate(sim_views, view_weights)
+            folded = (not self.training) and (not torch.is_grad_enabled()) and num_depth <= 64
+            if folded:
+                # inference: PixelwiseNet (BatchNorm folded) + aggregation in one kernel
+                view_weights, similarity = ops.pixelwise_aggregate(sim_views, ops.fold_pixelwise_net(self.pixel_wise_net))
+            else:
+                weights = [self.pixel_wise_net(sim_views[i].unsqueeze(1)) for i in range(sim_views.shape[0])]
+                view_weights = torch.cat(weights, dim=1)                   # [B,Nsrc,H,W]
+                similarity = ops.aggregate(sim_views, view_weights)
         else:
             similarity, _ = ops.cost_volume(ref_feature, src_features, rot_trans, depth_values, view_weights, False)
         similarity = similarity.unsqueeze(1)                               # [B,1,D,H,W]

@@ -181,6 +181,64 @@ def aggregate(sim_views: torch.Tensor, view_weights: torch.Tensor) -> torch.Tens
     return _Aggregate.apply(sim_views, view_weights)
 
 
+def depth_hypotheses(cur_depth: torch.Tensor, ndepth: int, depth_interval_pixel: float, image_hw: Tuple[int, int],
+                     stage_scale: int) -> torch.Tensor:
+    """Depth hypotheses of a cascade stage at the stage resolution.
+
+    One kernel for models/TransMVSNet.py:174-190 + 202-204: cur_depth is depth_values [B,192] (stage 1, the
+    2-D branch of get_depth_samples) or the previous stage's depth map [B,hp,wp] (bilinear upsample to the
+    image size, +- ndepth/2 * interval, trilinear resample to [ndepth, H/scale, W/scale]).
+    """
+    lib = _lib.load()
+    dev = _need_cuda(cur_depth)
+    cur = cur_depth.detach().contiguous()
+    b = cur.shape[0]
+    h, w = image_hw[0] // stage_scale, image_hw[1] // stage_scale
+    out = torch.empty((b, ndepth, h, w), dtype=torch.float32, device=dev)
+    planes, hp, wp = (cur.shape[1], 0, 0) if cur.dim() == 2 else (0, cur.shape[1], cur.shape[2])
+    with torch.cuda.device(dev):
+        rc = lib.tmvs_depth_hypotheses_fwd(_ptr(cur), planes, hp, wp, float(depth_interval_pixel), _ptr(out), b,
+                                           ndepth, h, w, int(stage_scale), _stream())
+    _lib.check(rc, "tmvs_depth_hypotheses_fwd")
+    return out
+
+
+def fold_pixelwise_net(pwn: torch.nn.Module) -> torch.Tensor:
+    """PixelwiseNet (models/TransMVSNet.py:10-30) -> 177 floats with the eval-mode BatchNorm folded into the
+    1x1x1 convolutions: w0[16], b0[16], w1[8,16], b1[8], w2[8], b2  (host tensor, passed by value)."""
+    def fold(conv_bn):
+        w = conv_bn.conv.weight.detach().double().flatten(1)                 # [out, in]
+        bn = conv_bn.bn
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        return w * scale[:, None], bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    w0, b0 = fold(pwn.conv0)
+    w1, b1 = fold(pwn.conv1)
+    w2 = pwn.conv2.weight.detach().double().flatten()
+    b2 = pwn.conv2.bias.detach().double().flatten()
+    flat = torch.cat([w0.flatten(), b0, w1.flatten(), b1, w2, b2]).float().cpu().contiguous()
+    assert flat.numel() == 177
+    return flat
+
+
+def pixelwise_aggregate(sim_views: torch.Tensor, folded_mlp: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode PixelwiseNet + aggregation in one kernel.
+
+    sim_views [N,B,D,H,W], folded_mlp = fold_pixelwise_net(net) -> (view_weights [B,N,H,W], agg [B,D,H,W]).
+    """
+    lib = _lib.load()
+    dev = _need_cuda(sim_views)
+    n, b, d, h, w = sim_views.shape
+    sim_views = sim_views.detach().contiguous()
+    mlp = folded_mlp.detach().to("cpu", torch.float32).contiguous()
+    vw = torch.empty((b, n, h, w), dtype=torch.float32, device=dev)
+    agg = torch.empty((b, d, h, w), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tmvs_pixelwise_aggregate_fwd(_ptr(sim_views), ctypes.c_void_p(mlp.data_ptr()), _ptr(vw), _ptr(agg),
+                                              b, d, h, w, n, _stream())
+    _lib.check(rc, "tmvs_pixelwise_aggregate_fwd")
+    return vw, agg
+
+
 def costvol_backward_packed(ref_fea: torch.Tensor, packed: torch.Tensor, rot_trans, depth_values: torch.Tensor,
                             grad_views: torch.Tensor, need_ref: bool = True, need_src: bool = True
                             ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
