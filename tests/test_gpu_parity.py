@@ -433,11 +433,12 @@ def test_pixelwise_aggregate_folded_kernel():
         bn.running_var.uniform_(0.5, 2.0)
         bn.weight.data.normal_(1, 0.2)
         bn.bias.data.normal_(0, 0.2)
-    net = net.eval().to(DEV)
+    net = net.eval()                  # the module on the CPU: cuDNN convolutions default to TF32 on the GPU
     with torch.no_grad():
-        want = torch.cat([net(views[i].unsqueeze(1)) for i in range(views.shape[0])], 1)
+        vc = views.cpu()
+        want = torch.cat([net(vc[i].unsqueeze(1)) for i in range(vc.shape[0])], 1)
     got, _ = tm.pixelwise_aggregate(views, tm.fold_pixelwise_net(net))
-    assert float((got - want).abs().max()) <= 1e-5
+    assert float((got.cpu() - want).abs().max()) <= 1e-5
 
 
 def test_depthnet_forward_learned_weights():
