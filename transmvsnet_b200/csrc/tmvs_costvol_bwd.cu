@@ -151,6 +151,21 @@ __device__ __forceinline__ void cswap(int &a, int &b)
     a = lo; b = hi;
 }
 
+// Registration uses RELAXED (morally strong) shared-memory stores and loads: several threads may store their id
+// to the same cell in the same round and exactly one value survives.  These are plain STS / LDS in SASS -- no
+// read-modify-write atomic -- but, unlike weak accesses, concurrent relaxed stores are not a data race in the
+// PTX memory model.
+__device__ __forceinline__ void st_relaxed_s32(int *p, int v)
+{
+    asm volatile("st.relaxed.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+
 constexpr int kGroup = 8;            // tiles per side of a scan group (8x8 tiles = 256x64 pixels)
 constexpr int kPlanes = 4;           // depth planes of one reference tile handled per registration round
 constexpr int kSlots2 = 4;           // footprints per cell per plane on the fast path
@@ -331,11 +346,11 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
                     for (int r = 0; r < kSlots2; ++r) {
 #pragma unroll
                         for (int pl = 0; pl < kPlanes; ++pl)
-                            if (pend & (1u << pl)) cell[pl][r][my_cell[pl]] = tid;
+                            if (pend & (1u << pl)) st_relaxed_s32(&cell[pl][r][my_cell[pl]], tid);
                         __syncthreads();
 #pragma unroll
                         for (int pl = 0; pl < kPlanes; ++pl)
-                            if ((pend & (1u << pl)) && cell[pl][r][my_cell[pl]] == tid) pend &= ~(1u << pl);
+                            if ((pend & (1u << pl)) && ld_relaxed_s32(&cell[pl][r][my_cell[pl]]) == tid) pend &= ~(1u << pl);
                         left = __syncthreads_or(pend != 0);
                         if (!left) break;
                     }
