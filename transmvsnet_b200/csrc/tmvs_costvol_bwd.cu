@@ -167,7 +167,19 @@ __device__ __forceinline__ int ld_relaxed_s32(const int *p)
 }
 
 constexpr int kGroup = 8;            // tiles per side of a scan group (8x8 tiles = 256x64 pixels)
-constexpr int kPlanes = 4;           // depth planes of one reference tile handled per registration round
+#ifndef TMVS_BWD_PLANES
+#define TMVS_BWD_PLANES 4
+#endif
+#ifndef TMVS_BWD_MINB8
+#define TMVS_BWD_MINB8 4
+#endif
+#ifndef TMVS_BWD_MINB4
+#define TMVS_BWD_MINB4 5
+#endif
+#ifndef TMVS_BWD_MINB2
+#define TMVS_BWD_MINB2 5
+#endif
+constexpr int kPlanes = TMVS_BWD_PLANES;   // depth planes of one reference tile handled per registration round
 constexpr int kSlots2 = 4;           // footprints per cell per plane on the fast path
 
 // Union over ALL planes of the boxes of the 8x8 tiles of a group: the coarse level of the scan.
@@ -200,8 +212,10 @@ bwd_gbox_kernel(const int4 *__restrict__ bbox, int4 *__restrict__ gbox, int D, i
     }
 }
 
+template <int C4T> struct BwdMinBlocks { static constexpr int value = C4T >= 8 ? TMVS_BWD_MINB8 : (C4T >= 4 ? TMVS_BWD_MINB4 : TMVS_BWD_MINB2); };
+
 template <int C4T, bool EXACT, bool PER_PIXEL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BwdMinBlocks<C4T>::value)
 bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth, const float *__restrict__ G,
                const int4 *__restrict__ bbox, const int4 *__restrict__ gbox, float *__restrict__ grad_src, int b_total,
                int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_tx, int n_ty, int n_tiles,
@@ -209,7 +223,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
 {
     __shared__ int cell[kPlanes][kSlots2][kCells];
     __shared__ float krec[kPlanes][4][kThreads];
-    __shared__ int x0rec[kPlanes][kThreads], y0rec[kPlanes][kThreads];
+    __shared__ int xyrec[kPlanes][kThreads];           // footprint origin, (y0 + 2) << 16 | (x0 + 2), for the exhaustive path
     __shared__ int pixrec[kThreads];
     __shared__ int hits[kThreads];
     __shared__ int ghits[kThreads];
@@ -330,7 +344,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
                         }
                         if (pl < run) {
                             krec[pl][0][tid] = k00; krec[pl][1][tid] = k01; krec[pl][2][tid] = k10; krec[pl][3][tid] = k11;
-                            x0rec[pl][tid] = x0; y0rec[pl][tid] = y0;
+                            xyrec[pl][tid] = x0 == kEmpty ? -1 : (((y0 + 2) << 16) | (x0 + 2));
                         }
                     }
                     for (int c = tid; c < run * kSlots2 * kCells; c += kThreads) (&cell[0][0][0])[c] = kEmpty;
@@ -380,10 +394,10 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
                                 // exhaustive, still ordered (class, then reference-pixel id)
 #pragma unroll 1
                                 for (int cls = 0; cls < 4; ++cls) {
-                                    const int want_x = qx - (cls & 1), want_y = qy - (cls >> 1);
+                                    const int want = ((qy - (cls >> 1) + 2) << 16) | (qx - (cls & 1) + 2);
 #pragma unroll 1
                                     for (int t2 = 0; t2 < kThreads; ++t2) {
-                                        if (x0rec[pl][t2] == want_x && y0rec[pl][t2] == want_y) {
+                                        if (xyrec[pl][t2] == want) {
                                             const float k = krec[pl][cls][t2];
                                             if (k != 0.0f) accumulate(k, pixrec[t2]);
                                         }
