@@ -48,6 +48,18 @@ enum {
 
 typedef void *tmvs_stream_t;
 
+/*
+ * The reference's own CPU and CUDA executions of models/module.py:311-313 differ in the last bit: ATen's CPU kernel
+ * divides by the python scalar (W-1)/2, ATen's CUDA kernel multiplies by its reciprocal.  At 1152x1600 that moves
+ * sample positions by ~1e-4 px and cost volumes by ~2e-4 (max-norm).  TMVS_ARITH_IEEE (default) follows the CPU
+ * arithmetic -- the one the golden vectors pin --; TMVS_ARITH_ATEN_CUDA follows the CUDA one.  Process-wide setting,
+ * read at launch time.
+ */
+#define TMVS_ARITH_IEEE 0
+#define TMVS_ARITH_ATEN_CUDA 1
+int tmvs_set_reference_arithmetic(int mode);
+int tmvs_get_reference_arithmetic(void);
+
 int tmvs_version(void);
 const char *tmvs_error_string(int code);
 

@@ -22,7 +22,7 @@
  * Build:  gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC   (see oracle/build.py)
  * -ffp-contract=off matters: the reference runs separate mul/add ATen kernels,
  * so every intermediate is rounded to fp32; only the 3-term dot product of the
- * rot @ xyz matmul is done with fmaf (BLAS implementations fuse it).
+ * rot @ xyz matmul uses fmaf, in the order sgemm does (see oracle_source_index).
  */
 #include <math.h>
 #include <stdint.h>
@@ -44,10 +44,11 @@ int tmvs_oracle_version(void) { return TMVS_ORACLE_VERSION; }
 static inline void oracle_source_index(const float *rt, float x, float y, float depth,
                                        int H, int W, float *ix, float *iy)
 {
-    /* module.py:305  rot_xyz = rot @ (x, y, 1) */
-    float rx = fmaf(rt[0], x, fmaf(rt[1], y, rt[2]));
-    float ry = fmaf(rt[3], x, fmaf(rt[4], y, rt[5]));
-    float rz = fmaf(rt[6], x, fmaf(rt[7], y, rt[8]));
+    /* module.py:305  rot_xyz = rot @ (x, y, 1).  sgemm (MKL and cuBLAS alike, probed bit for bit by
+       scripts/probe_matmul.py) accumulates in k order with FMAs: r0*x, fma(r1, y, .), fma(r2, 1, .) */
+    float rx = fmaf(rt[1], y, rt[0] * x) + rt[2];
+    float ry = fmaf(rt[4], y, rt[3] * x) + rt[5];
+    float rz = fmaf(rt[7], y, rt[6] * x) + rt[8];
     /* module.py:306-308  rot_depth_xyz = rot_xyz * depth ; proj_xyz = . + trans */
     float px = rx * depth; px = px + rt[9];
     float py = ry * depth; py = py + rt[10];

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_PKG, "lib", "libtmvs_sm100a.so")
 _P = c_void_p
 SIGNATURES = {
     "tmvs_version": (c_int, []),
+    "tmvs_set_reference_arithmetic": (c_int, [c_int]),
+    "tmvs_get_reference_arithmetic": (c_int, []),
     "tmvs_error_string": (ctypes.c_char_p, [c_int]),
     "tmvs_packed_bytes": (c_size_t, [c_int] * 5),
     "tmvs_pack_sources": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, _P]),

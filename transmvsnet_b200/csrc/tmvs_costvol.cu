@@ -97,7 +97,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     }
     float wsum = 1e-5f;                                // TransMVSNet.py:72
     const float inv_c = 1.0f / (float)C;
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float xf = (float)x, yf = (float)y;
 
@@ -308,6 +308,7 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
+        geom.arith = tmvs_arith_mode();
         for (int i = 0; i < n_src; ++i)
             for (int bl = 0; bl < bc; ++bl)
                 for (int k = 0; k < 12; ++k)

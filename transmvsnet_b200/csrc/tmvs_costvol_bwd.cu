@@ -48,7 +48,7 @@ bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ dept
     const float *rt = geom.rt[i * b_chunk + bl];
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const float inv_c = 1.0f / (float)C;
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;
     const float *gp = G + ((size_t)i * b_total + b) * D * HW + pix;
@@ -114,7 +114,7 @@ bwd_bbox_kernel(const float *__restrict__ depth, int4 *__restrict__ bbox, int b_
     const size_t HW = (size_t)H * W, pix = (size_t)min(y, H - 1) * W + min(x, W - 1);
     const float *rt = geom.rt[i * b_chunk + bl];
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const int tile = blockIdx.y * n_tx + blockIdx.x;
     int4 *out = bbox + ((size_t)blockIdx.z * n_tiles + tile) * D;
     const int warp = threadIdx.y, lane = threadIdx.x;
@@ -238,7 +238,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     const size_t HW = (size_t)H * W;
     const float *rt = geom.rt[i * b_chunk + bl];
     const float inv_c = 1.0f / (float)C;
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float4 *rimg = refp + (size_t)b * pk.slice;
     const float *gview = G + ((size_t)i * b_total + b) * D * HW;
@@ -516,6 +516,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
+        geom.arith = tmvs_arith_mode();
         for (int i = 0; i < n_src; ++i)
             for (int bl = 0; bl < bc; ++bl)
                 for (int k = 0; k < 12; ++k)

@@ -128,7 +128,7 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     }
     float wsum = 1e-5f;                                // TransMVSNet.py:72
     const float inv_c = 1.0f / (float)C;
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(C4T, H, W);
     const float xf = (float)x, yf = (float)y;
     unsigned phase = 0, round = 0;
@@ -375,6 +375,7 @@ int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, i
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
+        geom.arith = tmvs_arith_mode();
         for (int i = 0; i < n_src; ++i)
             for (int bl = 0; bl < bc; ++bl)
                 for (int k = 0; k < 12; ++k)

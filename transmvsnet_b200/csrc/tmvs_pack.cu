@@ -140,7 +140,7 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
     const size_t pix = (size_t)y * W + x;
     const float *rt = geom.rt[bl];
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
-    const TmvsDims dims = tmvs_dims(H, W);
+    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float4 *img = packed + (size_t)b * pk.slice;
 #pragma unroll
@@ -238,6 +238,7 @@ extern "C" int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_tra
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
+        geom.arith = tmvs_arith_mode();
         for (int bl = 0; bl < bc; ++bl)
             for (int k = 0; k < 12; ++k) geom.rt[bl][k] = rot_trans[(size_t)(b0 + bl) * 12 + k];
         dim3 grid((W + 31) / 32, (H + 7) / 8, bc * n_dchunks);

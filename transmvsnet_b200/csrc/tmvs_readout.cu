@@ -369,6 +369,18 @@ extern "C" int tmvs_depth_hypotheses_fwd(const float *prev_depth, int prev_plane
     return tmvs_launch_status();
 }
 
+static int g_arith_mode = TMVS_ARITH_IEEE;
+int tmvs_arith_mode() { return g_arith_mode; }
+
+extern "C" int tmvs_set_reference_arithmetic(int mode)
+{
+    if (mode != TMVS_ARITH_IEEE && mode != TMVS_ARITH_ATEN_CUDA) return TMVS_E_UNSUPPORTED;
+    g_arith_mode = mode;
+    return TMVS_OK;
+}
+
+extern "C" int tmvs_get_reference_arithmetic(void) { return g_arith_mode; }
+
 extern "C" int tmvs_version(void) { return TMVS_VERSION; }
 
 extern "C" const char *tmvs_error_string(int code)

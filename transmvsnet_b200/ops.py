@@ -19,6 +19,13 @@ from . import _lib
 from .geometry import relative_rot_trans
 
 
+def set_reference_arithmetic(which: str) -> None:
+    """"cpu" (default): follow ATen's CPU arithmetic (IEEE division by (W-1)/2), the one the golden vectors pin;
+    "cuda": follow ATen's CUDA arithmetic (multiply by the reciprocal) -- see include/tmvs.h."""
+    mode = {"cpu": 0, "ieee": 0, "cuda": 1}[which]
+    _lib.check(_lib.load().tmvs_set_reference_arithmetic(mode), "tmvs_set_reference_arithmetic")
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
