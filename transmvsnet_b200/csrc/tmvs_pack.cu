@@ -38,8 +38,15 @@ pack_sources_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
 }
 
 // NCHW fast path (x contiguous, W % 4 == 0, 16-byte aligned rows): one thread moves a 4-pixel x 4-channel
-// block -- four 128-bit loads (one per channel plane), a register transpose, four 128-bit stores.
-__global__ void __launch_bounds__(256)
+// block of TMVS_PACK_G consecutive channel groups -- 4 * G independent 128-bit streaming loads (one per channel
+// plane), a register transpose, 4 * G 128-bit stores.
+#ifndef TMVS_PACK_G
+#define TMVS_PACK_G 2
+#endif
+#ifndef TMVS_PACK_THREADS
+#define TMVS_PACK_THREADS 128
+#endif
+__global__ void __launch_bounds__(TMVS_PACK_THREADS)
 pack_sources_nchw4_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float4 *__restrict__ packed,
                           int B, int C, int c4, int H, int W)
 {
@@ -47,23 +54,32 @@ pack_sources_nchw4_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float
     const size_t nquads = (size_t)H * wq;
     const size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qd >= nquads) return;
-    const int g = blockIdx.y;
+    const int g0 = blockIdx.y * TMVS_PACK_G;
     const int vb = blockIdx.z;
     const int view = vb / B, b = vb - view * B;
     const int y = (int)(qd / wq), xq = (int)(qd - (size_t)y * wq);
     const float *base = src.p[view] + b * sB + y * sH + 4 * xq;
-    float4 v[4];
+    float4 v[TMVS_PACK_G][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = 4 * g + j;
-        v[j] = (c < C) ? __ldg(reinterpret_cast<const float4 *>(base + c * sC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int gg = 0; gg < TMVS_PACK_G; ++gg) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * (g0 + gg) + j;
+            v[gg][j] = (c < C) ? __ldcs(reinterpret_cast<const float4 *>(base + c * sC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
-    float4 *o = packed + (size_t)vb * pk.slice + tmvs_pk_off(pk, 4 * xq, y * pk.row) + g * 8;   // 4 | 8: same block
-    o[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
-    o[1] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-    o[2] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
-    o[3] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+    float4 *o0 = packed + (size_t)vb * pk.slice + tmvs_pk_off(pk, 4 * xq, y * pk.row);   // 4 | 8: same block
+#pragma unroll
+    for (int gg = 0; gg < TMVS_PACK_G; ++gg) {
+        if (g0 + gg < c4) {
+            float4 *o = o0 + (g0 + gg) * 8;
+            o[0] = make_float4(v[gg][0].x, v[gg][1].x, v[gg][2].x, v[gg][3].x);
+            o[1] = make_float4(v[gg][0].y, v[gg][1].y, v[gg][2].y, v[gg][3].y);
+            o[2] = make_float4(v[gg][0].z, v[gg][1].z, v[gg][2].z, v[gg][3].z);
+            o[3] = make_float4(v[gg][0].w, v[gg][1].w, v[gg][2].w, v[gg][3].w);
+        }
+    }
 }
 
 // NCHW fast path for W % 8 == 0: one thread moves a whole 8-pixel block of one channel group -- eight
@@ -212,8 +228,8 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
     // (pack_sources_nchw8_kernel, a whole 128-byte line per thread, measured ~8 % SLOWER than the 4-pixel kernel
     //  on B200 -- 3.4-3.6 vs 3.7-3.9 TB/s -- so it is kept for reference but not dispatched)
     if (aligned && sW == 1 && (W & 3) == 0 && (sH & 3) == 0 && (sC & 3) == 0 && (sB & 3) == 0) {
-        dim3 grid((unsigned)((HW / 4 + 255) / 256), c4, n_src * B);
-        pack_sources_nchw4_kernel<<<grid, 256, 0, st>>>(ptrs, sB, sC, sH, (float4 *)packed, B, C, c4, H, W);
+        dim3 grid((unsigned)((HW / 4 + TMVS_PACK_THREADS - 1) / TMVS_PACK_THREADS), (c4 + TMVS_PACK_G - 1) / TMVS_PACK_G, n_src * B);
+        pack_sources_nchw4_kernel<<<grid, TMVS_PACK_THREADS, 0, st>>>(ptrs, sB, sC, sH, (float4 *)packed, B, C, c4, H, W);
     } else if (aligned && sC == 1 && (C & 3) == 0 && (sW & 3) == 0 && (sH & 3) == 0 && (sB & 3) == 0) {
         dim3 grid((unsigned)((HW + 255) / 256), c4, n_src * B);
         pack_sources_nhwc_kernel<<<grid, 256, 0, st>>>(ptrs, sB, sH, sW, (float4 *)packed, B, c4, H, W);
