@@ -119,6 +119,20 @@ int tmvs_depth_hypotheses_fwd(const float *prev_depth, int prev_planes, int hp, 
                               int B, int D, int h, int w, int scale, tmvs_stream_t stream);
 
 /*
+ * SURVEY.md 8(f) N3 -- read-out -> wire format on the device (test.py:119-158, utils.py:11-21): the stage-1/2
+ * confidence maps are bilinearly resized to the stage-3 size (cv2.resize INTER_LINEAR semantics), multiplied into
+ * the final confidence, depth is zeroed where confidence < threshold, and the 8-bit alpha channel the PNG carries
+ * (depth_normal: clamp to [depth_min, depth_max], scale to 0..255, truncate) is produced -- so only two float maps
+ * and one byte map cross PCIe instead of every output including prob_volume (utils.py:66-73 tensor2numpy).
+ *   depth, conf3 [B][H][W]; conf1 [B][h1][w1]; conf2 [B][h2][w2]
+ *   depth_out, conf_out [B][H][W] fp32; alpha_out [B][H][W] uint8   (any output may be NULL)
+ */
+int tmvs_finalize_maps_fwd(const float *depth, const float *conf3, const float *conf1, int h1, int w1,
+                           const float *conf2, int h2, int w2, float conf_threshold, float depth_min,
+                           float depth_max, float *depth_out, float *conf_out, uint8_t *alpha_out, int B, int H,
+                           int W, tmvs_stream_t stream);
+
+/*
  * SURVEY.md 8(f) N2 -- eval-mode PixelwiseNet folded into the aggregation (models/TransMVSNet.py:10-30, 82-93):
  * for every source view   w_i = max_d sigmoid(MLP(sim_i[d])),  MLP = 1->16->8->1 per-voxel (1x1x1 Conv3d with the
  * BatchNorm3d running statistics folded in, ReLU),  then  agg = sum_i sim_i*w_i / (1e-5 + sum_i w_i).

@@ -193,7 +193,33 @@ def hypotheses_case():
     save("hypotheses", **arrays)
 
 
+def finalize_case():
+    """test.py:126-144 (cv2.resize of the stage-1/2 confidences, product, depth[conf < 0.01] = 0) followed by the
+    reference's utils.depth_normal -- the numpy/cv2 statements of save_depth, run as they stand."""
+    import cv2
+    from utils import depth_normal      # reference utils.py:11-21
+    g = torch.Generator().manual_seed(61)
+    b, h, w = 2, 40, 56
+    depth = (400 + 560 * torch.rand(b, h, w, generator=g)).numpy()          # some beyond [425, 935]
+    conf3 = torch.rand(b, h, w, generator=g).numpy() ** 2
+    conf2 = torch.rand(b, h // 2, w // 2, generator=g).numpy()
+    conf1 = torch.rand(b, h // 4, w // 4, generator=g).numpy()
+    d_out, c_out, a_out = [], [], []
+    for i in range(b):
+        c1 = cv2.resize(conf1[i], (w, h))
+        c2 = cv2.resize(conf2[i], (w, h))
+        conf_final = conf3[i] * c1 * c2
+        d = depth[i].copy()
+        d[conf_final < 0.01] = 0.0
+        d_out.append(d.copy())
+        c_out.append(conf_final)
+        a_out.append(depth_normal(d, depth_min=425.0, depth_max=935.0))
+    save("finalize", depth=depth, conf3=conf3, conf2=conf2, conf1=conf1, depth_out=np.stack(d_out),
+         conf_out=np.stack(c_out), alpha_out=np.stack(a_out))
+
+
 if __name__ == "__main__":
+    finalize_case()
     hypotheses_case()
     warp_cases()
     depthnet_cases()

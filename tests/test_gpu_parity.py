@@ -393,6 +393,19 @@ def test_depthnet_forward_given_weights(name):
     assert np.abs(out["photo_confidence"].cpu().numpy() - g["photo_confidence"]).max() <= 5e-5
 
 
+def test_finalize_maps_wire_format():
+    """confidence product + cv2-style resize + masking + 8-bit depth, against the reference's own
+    numpy/cv2 statements (golden)."""
+    g = golden("finalize")
+    d, c, a = tm.finalize_maps(cu(g["depth"]), cu(g["conf3"]), cu(g["conf1"]), cu(g["conf2"]))
+    c_ref, d_ref, a_ref = g["conf_out"], g["depth_out"], g["alpha_out"]
+    assert np.abs(c.cpu().numpy() - c_ref).max() <= 1e-6
+    near_thr = np.abs(c_ref - 0.01) <= 1e-6                                 # a last-bit difference may flip the mask
+    assert np.array_equal(d.cpu().numpy()[~near_thr], d_ref[~near_thr])
+    assert a.dtype == torch.uint8 and np.array_equal(a.cpu().numpy()[~near_thr], a_ref[~near_thr])   # bytes: bit-exact
+    assert near_thr.mean() < 1e-3
+
+
 def test_depth_hypotheses_kernel():
     """stage hypotheses in one kernel against the reference's interpolate -> get_depth_samples ->
     interpolate chain (golden), and against the torch port at the DTU image size (stage 2)."""

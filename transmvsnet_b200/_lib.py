@@ -25,6 +25,8 @@ SIGNATURES = {
     "tmvs_costvol_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P,
                                  c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_aggregate_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "tmvs_finalize_maps_fwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "tmvs_depth_hypotheses_fwd": (c_int, [_P, c_int, c_int, c_int, ctypes.c_float, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_pixelwise_aggregate_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_costvol_bwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P,

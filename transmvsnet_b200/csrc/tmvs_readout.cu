@@ -282,6 +282,63 @@ depth_hypotheses_kernel(const float *__restrict__ prev, int prev_planes, int hp,
     }
 }
 
+// cv2.resize(..., INTER_LINEAR) tap of a float32 map: source index / weight exactly as OpenCV forms them
+// (fx = (float)((dx + 0.5) * scale - 0.5), scale = src / dst in double; borders replicate)
+struct CvTap {
+    int i0, i1;
+    float a0, a1;
+};
+
+__device__ __forceinline__ CvTap cv_tap(int d, int src, int dst)
+{
+    const double scale = (double)src / (double)dst;
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { f = 0.0f; s = 0; }
+    if (s >= src - 1) { f = 0.0f; s = src - 1; }
+    CvTap t;
+    t.i0 = s;
+    t.i1 = min(s + 1, src - 1);
+    t.a0 = 1.0f - f;
+    t.a1 = f;
+    return t;
+}
+
+__device__ __forceinline__ float cv_bilinear(const float *__restrict__ m, int h, int w, int y, int x, int H, int W)
+{
+    const CvTap tx = cv_tap(x, w, W), ty = cv_tap(y, h, H);
+    // OpenCV: horizontal pass per source row, then the vertical blend
+    const float r0 = __fadd_rn(__fmul_rn(__ldg(m + (size_t)ty.i0 * w + tx.i0), tx.a0), __fmul_rn(__ldg(m + (size_t)ty.i0 * w + tx.i1), tx.a1));
+    const float r1 = __fadd_rn(__fmul_rn(__ldg(m + (size_t)ty.i1 * w + tx.i0), tx.a0), __fmul_rn(__ldg(m + (size_t)ty.i1 * w + tx.i1), tx.a1));
+    return __fadd_rn(__fmul_rn(r0, ty.a0), __fmul_rn(r1, ty.a1));
+}
+
+__global__ void __launch_bounds__(256)
+finalize_maps_kernel(const float *__restrict__ depth, const float *__restrict__ conf3, const float *__restrict__ conf1,
+                     int h1, int w1, const float *__restrict__ conf2, int h2, int w2, float thr, float dmin, float dmax,
+                     float *__restrict__ depth_out, float *__restrict__ conf_out, uint8_t *__restrict__ alpha_out,
+                     int H, int W)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int b = blockIdx.z;
+    const size_t p = ((size_t)b * H + y) * W + x;
+    const float c1 = cv_bilinear(conf1 + (size_t)b * h1 * w1, h1, w1, y, x, H, W);
+    const float c2 = cv_bilinear(conf2 + (size_t)b * h2 * w2, h2, w2, y, x, H, W);
+    const float cf = __fmul_rn(__fmul_rn(__ldg(conf3 + p), c1), c2);       // test.py:132
+    float d = __ldg(depth + p);
+    if (cf < thr) d = 0.0f;                                                  // test.py:144
+    if (depth_out) depth_out[p] = d;
+    if (conf_out) conf_out[p] = cf;
+    if (alpha_out) {                                                         // utils.py:11-21 depth_normal
+        float q = d < dmin ? dmin : d;
+        q = q > dmax ? dmax : q;
+        const float sc = __fmul_rn(__fdiv_rn(__fsub_rn(q, dmin), __fsub_rn(dmax, dmin)), 255.0f);
+        alpha_out[p] = (uint8_t)(int)sc;
+    }
+}
+
 inline bool bad_dims(int B, int D, int H, int W)
 {
     return B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535 || D > TMVS_MAX_DEPTH;
@@ -353,6 +410,21 @@ extern "C" int tmvs_depth_regression_bwd(const float *grad_depth, const float *d
         depth_regression_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
     else
         depth_regression_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(grad_depth, depth_values, grad_p, D, HW);
+    return tmvs_launch_status();
+}
+
+extern "C" int tmvs_finalize_maps_fwd(const float *depth, const float *conf3, const float *conf1, int h1, int w1,
+                                      const float *conf2, int h2, int w2, float conf_threshold, float depth_min,
+                                      float depth_max, float *depth_out, float *conf_out, uint8_t *alpha_out, int B,
+                                      int H, int W, tmvs_stream_t stream)
+{
+    if (!depth || !conf3 || !conf1 || !conf2) return TMVS_E_NULL;
+    if (!depth_out && !conf_out && !alpha_out) return TMVS_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || h1 <= 0 || w1 <= 0 || h2 <= 0 || w2 <= 0 || B > 65535) return TMVS_E_SHAPE;
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    finalize_maps_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(depth, conf3, conf1, h1, w1, conf2, h2, w2,
+                                                                        conf_threshold, depth_min, depth_max, depth_out,
+                                                                        conf_out, alpha_out, H, W);
     return tmvs_launch_status();
 }
 

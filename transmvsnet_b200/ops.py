@@ -210,6 +210,29 @@ def depth_hypotheses(cur_depth: torch.Tensor, ndepth: int, depth_interval_pixel:
     return out
 
 
+def finalize_maps(depth: torch.Tensor, conf3: torch.Tensor, conf1: torch.Tensor, conf2: torch.Tensor,
+                  conf_threshold: float = 0.01, depth_min: float = 425.0, depth_max: float = 935.0):
+    """Read-out -> wire format on the device (test.py:119-158, utils.py:11-21).
+
+    depth, conf3 [B,H,W]; conf1 [B,H/4,W/4]; conf2 [B,H/2,W/2] ->
+    (masked depth [B,H,W], final confidence [B,H,W], 8-bit alpha [B,H,W] uint8).
+    """
+    lib = _lib.load()
+    dev = _need_cuda(depth, conf3, conf1, conf2)
+    b, h, w = depth.shape
+    depth, conf3, conf1, conf2 = (t.detach().contiguous() for t in (depth, conf3, conf1, conf2))
+    d_out = torch.empty_like(depth)
+    c_out = torch.empty_like(depth)
+    a_out = torch.empty((b, h, w), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tmvs_finalize_maps_fwd(_ptr(depth), _ptr(conf3), _ptr(conf1), conf1.shape[1], conf1.shape[2],
+                                        _ptr(conf2), conf2.shape[1], conf2.shape[2], float(conf_threshold),
+                                        float(depth_min), float(depth_max), _ptr(d_out), _ptr(c_out), _ptr(a_out),
+                                        b, h, w, _stream())
+    _lib.check(rc, "tmvs_finalize_maps_fwd")
+    return d_out, c_out, a_out
+
+
 def fold_pixelwise_net(pwn: torch.nn.Module) -> torch.Tensor:
     """PixelwiseNet (models/TransMVSNet.py:10-30) -> 177 floats with the eval-mode BatchNorm folded into the
     1x1x1 convolutions: w0[16], b0[16], w1[8,16], b1[8], w2[8], b2  (host tensor, passed by value)."""
