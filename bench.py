@@ -113,8 +113,9 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
-def cpu_hot_path_time(workload: dict, steps: int, warmup: int):
-    """The reference's PyTorch CPU op sequence (oracle/torch_port.py) on a bounded sample of the workload."""
+def cpu_hot_path_time(workload: dict, steps: int, warmup: int, min_seconds: float = 0.0):
+    """The reference's PyTorch CPU op sequence (oracle/torch_port.py) on a bounded sample of the workload.
+    Runs `steps` timed passes, then keeps going until `min_seconds` of timed CPU work have accumulated."""
     import torch
     from oracle import torch_port
     from transmvsnet_b200 import synthetic
@@ -129,7 +130,7 @@ def cpu_hot_path_time(workload: dict, steps: int, warmup: int):
             for st in stages:
                 torch_port.hot_path(st)
         times = []
-        for _ in range(steps):
+        while len(times) < steps or sum(times) < min_seconds:
             t0 = time.perf_counter()
             for st in stages:
                 torch_port.hot_path(st)
@@ -294,7 +295,8 @@ def run_tmvs_arm(args, workload):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         e2e = {"value": world * vv * k_e2e / (ms * 1e-3), "unit": "voxel-views/s",
-               "h2d_bytes_per_step": sum(pipeline.stage_h2d_bytes(s) for s in host),
+               "h2d_bytes_per_step": sum(pipeline.stage_h2d_bytes(s, n == 0) for n, s in enumerate(host)),
+               "h2d_what": "features + logits + stage-1 view weights + depth seeds; hypotheses generated on device",
                "d2h_bytes_per_step": pipeline.HostPipeline.d2h_bytes(host), "steps": k_e2e,
                "ms_per_step": ms / k_e2e}
     sampler.stop_flag.set()
@@ -302,8 +304,10 @@ def run_tmvs_arm(args, workload):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cvv, times, cores, sample = cpu_hot_path_time(workload, steps=2, warmup=1)
-        cpu = {"value": cvv / min(times), "unit": "voxel-views/s", "cores": cores, "kind": "port", "sample": sample}
+        cvv, times, cores, sample = cpu_hot_path_time(workload, steps=3, warmup=1, min_seconds=10.0)
+        cpu = {"value": cvv * len(times) / sum(times), "unit": "voxel-views/s", "cores": cores, "kind": "port",
+               "sample": sample + f"; {len(times)} passes, {sum(times):.1f} s of CPU work",
+               "best_pass_value": cvv / min(times)}
 
     if rank == 0:
         line = {

@@ -393,6 +393,24 @@ def test_depthnet_forward_given_weights(name):
     assert np.abs(out["photo_confidence"].cpu().numpy() - g["photo_confidence"]).max() <= 5e-5
 
 
+def test_host_pipeline_end_to_end():
+    """The end-to-end form bench.py times: pinned host inputs -> H2D -> N1 hypotheses -> pack / cost volume /
+    read-out -> D2H, against the oracle fed with the torch-port hypotheses."""
+    from oracle import torch_port
+    host = [pipeline.pin_stage(s) for s in synthetic.make_cascade(batch=1, n_views=3, height=96, width=160, seed=17)]
+    pipe = pipeline.HostPipeline(DEV)
+    for _ in range(2):                                   # second call reuses the persistent buffers / events
+        res = pipe.process_view(host)
+        torch.cuda.synchronize()
+    for st, r in zip(host, res):
+        scale = pipeline.synthetic_scale(st)
+        hyp = torch_port.depth_hypotheses(st.cur_depth, st.num_depth, st.interval_pixel, st.image_hw, scale)
+        _, o_idx, o_dep, o_conf = oracle.softmax_wta(st.logits, hyp, want_prob=False)
+        rng = float(hyp.max() - hyp.min())
+        assert np.abs(r["depth"].numpy() - o_dep).max() <= DEPTH_FRAC * rng
+        assert np.abs(r["photo_confidence"].numpy() - o_conf).max() <= PROB_ABS
+
+
 def test_finalize_maps_wire_format():
     """confidence product + cv2-style resize + masking + 8-bit depth, against the reference's own
     numpy/cv2 statements (golden)."""

@@ -33,6 +33,11 @@ class StageInputs:
     view_weights: torch.Tensor            # [B,Nsrc,h,w]
     logits: torch.Tensor                  # [B,D,h,w] stand-in for the 3-D CNN output
     num_depth: int = 0
+    # what the cascade actually holds before it builds depth_values (models/TransMVSNet.py:174-190): the 192 global
+    # planes (stage 1) or the previous stage's depth map; with interval_pixel and image_hw they regenerate hypotheses
+    cur_depth: Optional[torch.Tensor] = None
+    interval_pixel: float = 0.0
+    image_hw: tuple = (0, 0)
 
     @property
     def voxel_views(self) -> int:
@@ -119,6 +124,7 @@ def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 11
     dv = cams["depth_values"]                                # [B,192]
     d_min, d_max = dv[:, 0], dv[:, -1]
     depth_interval = (d_max - d_min) / dv.shape[1]           # models/TransMVSNet.py:149
+    cur_depth = dv
     if stage == 1:
         # models/module.py:616-623 (2-D branch): the global range split into D planes
         new_int = (d_max - d_min) / (d - 1)
@@ -138,6 +144,12 @@ def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 11
         new_int = (cur_max - cur_min) / (d - 1)
         hyp = cur_min[:, None] + torch.arange(d, dtype=torch.float32)[None, :, None, None] * new_int[:, None]
         hyp = hyp.contiguous()
+        # the same surface at the previous stage's resolution: what the cascade would carry over
+        hp, wp = height // STAGES[stage - 2][2], width // STAGES[stage - 2][2]
+        yy = torch.linspace(0, 1, hp)[:, None]
+        xx = torch.linspace(0, 1, wp)[None, :]
+        cur_depth = (mid + 0.25 * span * torch.sin(3.0 * math.pi * xx) * torch.cos(2.0 * math.pi * yy)[None]
+                     + 0.1 * span * (xx - 0.5)[None]).float().contiguous()
     feats = [torch.randn(batch, c, h, w, generator=g) for _ in range(n_views)]
     if stage1_weights is None:
         h1, w1 = height // STAGES[0][2], width // STAGES[0][2]
@@ -151,7 +163,9 @@ def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 11
     vw = vw[:, :, :h, :w].contiguous()
     logits = 3.0 * torch.randn(batch, d, h, w, generator=g)
     return StageInputs(stage=stage, features=feats, proj_matrix=cams[f"stage{stage}"],
-                       depth_values=hyp.float(), view_weights=vw, logits=logits, num_depth=d)
+                       depth_values=hyp.float(), view_weights=vw, logits=logits, num_depth=d,
+                       cur_depth=cur_depth.float().contiguous(),
+                       interval_pixel=float(DEPTH_RATIOS[stage - 1] * depth_interval[0]), image_hw=(height, width))
 
 
 def make_cascade(*, batch: int = 1, n_views: int = 5, height: int = 1152, width: int = 1600,
