@@ -85,6 +85,30 @@ def test_forward_and_backward_beat_stock_pytorch_cuda():
         torch.cuda.empty_cache()
         assert ours_ms * 3.0 < stock_ms, rows[-1]
         assert ours_fb < stock_fb, rows[-1]
+    # ---- stage 1 as the cascade runs it at inference: view weights LEARNED by PixelwiseNet (TransMVSNet.py:82-84)
+    import transmvsnet_b200 as tm
+    st = synthetic.make_stage(1, batch=1, n_views=5, height=1152, width=1600, seed=0)
+    dev = pipeline.stage_to_device(st, DEV)
+    pm = st.proj_matrix.to(DEV)
+    net = tm.DepthNet().to(DEV).eval()
+    ident = torch.nn.Identity()
+
+    def ours_stage1():
+        with torch.no_grad():
+            return net(dev["features"], pm, dev["depth_values"], st.num_depth, ident, view_weights=None)
+
+    def stock_stage1():
+        with torch.no_grad():
+            _, per_view = torch_port.cost_volume(dev["features"], pm, dev["depth_values"], None)
+            ws = [net.pixel_wise_net(s) for s in per_view]                  # the PyTorch module, cuDNN convolutions
+            num = sum(s * w.unsqueeze(1) for s, w in zip(per_view, ws))
+            den = 1e-5 + sum(w.unsqueeze(1) for w in ws)
+            return torch_port.read_out((num / den).squeeze(1), dev["depth_values"])
+
+    o_ms, s_ms = _time(ours_stage1, reps=3), _time(stock_stage1, reps=2)
+    rows.append({"stage": "1, learned view weights (DepthNet.forward, eval)",
+                 "forward_ms": {"tmvs": round(o_ms, 3), "stock_pytorch_cuda": round(s_ms, 3)}})
+    assert o_ms * 5.0 < s_ms, rows[-1]
     out = os.path.join(REPO, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, "stock_cuda_timing.json"), "w") as f:

@@ -29,7 +29,6 @@ namespace {
 
 constexpr int kTX = 32, kTY = 8, kThreads = kTX * kTY;
 constexpr int kCellW = kTX + 1, kCellH = kTY + 1, kCells = kCellW * kCellH;
-constexpr int kSlots = 4;          // footprints sharing one north-west pixel handled by the fast path
 constexpr int kEmpty = 0x7fffffff;
 
 // --------------------------------------------------------------------------------------------- grad_ref

@@ -82,45 +82,6 @@ pack_sources_nchw4_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float
     }
 }
 
-// NCHW fast path for W % 8 == 0: one thread moves a whole 8-pixel block of one channel group -- eight
-// independent 128-bit streaming loads (two per channel plane), a register transpose, one full 128-byte line out.
-__global__ void __launch_bounds__(256)
-pack_sources_nchw8_kernel(SrcPtrs src, int64_t sB, int64_t sC, int64_t sH, float4 *__restrict__ packed,
-                          int B, int C, int c4, int H, int W)
-{
-    const int wb = W >> 3;
-    const size_t nblocks = (size_t)H * wb;
-    const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blk >= nblocks) return;
-    const int g = blockIdx.y;
-    const int vb = blockIdx.z;
-    const int view = vb / B, b = vb - view * B;
-    const int y = (int)(blk / wb), xb = (int)(blk - (size_t)y * wb);
-    const float *base = src.p[view] + b * sB + y * sH + 8 * xb;
-    float4 lo[4], hi[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = 4 * g + j;
-        if (c < C) {
-            const float4 *p = reinterpret_cast<const float4 *>(base + c * sC);
-            lo[j] = __ldcs(p);
-            hi[j] = __ldcs(p + 1);
-        } else {
-            lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hi[j] = lo[j];
-        }
-    }
-    float4 *o = packed + ((size_t)vb * H * wb + blk) * (size_t)(c4 * 8) + g * 8;
-    o[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
-    o[1] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
-    o[2] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
-    o[3] = make_float4(lo[0].w, lo[1].w, lo[2].w, lo[3].w);
-    o[4] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
-    o[5] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
-    o[6] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
-    o[7] = make_float4(hi[0].w, hi[1].w, hi[2].w, hi[3].w);
-}
-
 // channels_last fast path (channel stride 1, C % 4 == 0, aligned): a pure 128-bit permuting copy.
 __global__ void __launch_bounds__(256)
 pack_sources_nhwc_kernel(SrcPtrs src, int64_t sB, int64_t sH, int64_t sW, float4 *__restrict__ packed,
@@ -225,8 +186,8 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
     bool aligned = true;
     for (int i = 0; i < n_src; ++i) aligned = aligned && (((uintptr_t)src[i] & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    // (pack_sources_nchw8_kernel, a whole 128-byte line per thread, measured ~8 % SLOWER than the 4-pixel kernel
-    //  on B200 -- 3.4-3.6 vs 3.7-3.9 TB/s -- so it is kept for reference but not dispatched)
+    // (a whole-line variant -- 8 pixels per thread -- measured ~8 % slower on B200 and was dropped; two channel
+    //  groups per thread and 128-thread CTAs measured 13 % faster: scripts/tune_pack.py)
     if (aligned && sW == 1 && (W & 3) == 0 && (sH & 3) == 0 && (sC & 3) == 0 && (sB & 3) == 0) {
         dim3 grid((unsigned)((HW / 4 + TMVS_PACK_THREADS - 1) / TMVS_PACK_THREADS), (c4 + TMVS_PACK_G - 1) / TMVS_PACK_G, n_src * B);
         pack_sources_nchw4_kernel<<<grid, TMVS_PACK_THREADS, 0, st>>>(ptrs, sB, sC, sH, (float4 *)packed, B, C, c4, H, W);

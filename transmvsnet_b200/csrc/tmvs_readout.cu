@@ -266,19 +266,26 @@ depth_hypotheses_kernel(const float *__restrict__ prev, int prev_planes, int hp,
     const int off = scale == 1 ? 0 : scale / 2 - 1;           // first of the two blended pixels
     const int n = scale == 1 ? 1 : 2;
     const float half_span = (float)D / 2.0f * interval;
-    for (int d = 0; d < D; ++d) {
-        float acc_y[2] = {0.0f, 0.0f};
-        for (int j = 0; j < n; ++j) {
-            float vx[2] = {0.0f, 0.0f};
-            for (int i = 0; i < n; ++i) {
-                const float up = upsampled_prev(pv, hp, wp, ry, rx, y * scale + off + j, x * scale + off + i);
-                const float cur_min = up - half_span, cur_max = up + half_span;
-                const float step = (cur_max - cur_min) / (float)(D - 1);
-                vx[i] = cur_min + (float)d * step;
-            }
-            acc_y[j] = n == 1 ? vx[0] : 0.5f * vx[0] + 0.5f * vx[1];
+    // the (up to) four upsampled depths this output pixel blends do not depend on the plane: fetch them once
+    float lo[2][2], st[2][2];
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            const float up = upsampled_prev(pv, hp, wp, ry, rx, y * scale + off + j, x * scale + off + i);
+            const float cur_min = up - half_span, cur_max = up + half_span;
+            lo[j][i] = cur_min;
+            st[j][i] = (cur_max - cur_min) / (float)(D - 1);
         }
-        o[(size_t)d * hw] = n == 1 ? acc_y[0] : 0.5f * acc_y[0] + 0.5f * acc_y[1];
+    for (int d = 0; d < D; ++d) {
+        const float fd = (float)d;
+        float v;
+        if (n == 1) {
+            v = lo[0][0] + fd * st[0][0];
+        } else {
+            const float r0 = 0.5f * (lo[0][0] + fd * st[0][0]) + 0.5f * (lo[0][1] + fd * st[0][1]);
+            const float r1 = 0.5f * (lo[1][0] + fd * st[1][0]) + 0.5f * (lo[1][1] + fd * st[1][1]);
+            v = 0.5f * r0 + 0.5f * r1;
+        }
+        __stcs(o + (size_t)d * hw, v);
     }
 }
 
