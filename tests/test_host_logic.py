@@ -62,6 +62,18 @@ def test_missing_library_fails_loudly(monkeypatch):
         _lib.load()
 
 
+def test_depthnet_fold_cache_tracks_parameter_updates():
+    net = tm.DepthNet().eval()
+    a = net._folded_mlp()
+    assert net._folded_mlp() is a                                   # cached
+    with torch.no_grad():
+        net.pixel_wise_net.conv2.bias.add_(1.0)                      # in-place update bumps the version counter
+    b = net._folded_mlp()
+    assert b is not a and float(b[-1] - a[-1]) == pytest.approx(1.0)
+    net.load_state_dict(tm.DepthNet().state_dict())
+    assert net._folded_mlp() is not b
+
+
 def test_depthnet_state_dict_keys_match_reference():
     g = golden("depthnet_s1_learned")
     ref_keys = sorted(k[4:] for k in g if k.startswith("pwn."))

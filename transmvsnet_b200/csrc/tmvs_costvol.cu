@@ -212,49 +212,35 @@ struct PwnParams {
     float w0[16], b0[16], w1[8][16], b1[8], w2[8], b2;
 };
 
-// PixelwiseNet (eval, BatchNorm folded) + aggregation: one thread per pixel and depth chunk would need the
-// max over ALL planes first, so a thread owns a pixel: sweep 1 per view finds max_d MLP(sim) (sigmoid is
-// monotone: one sigmoid per view), sweep 2 re-reads the D similarities (L1/L2 resident) into the accumulators.
-template <int DT>
-__global__ void __launch_bounds__(128)
-pixelwise_aggregate_kernel(const float *__restrict__ sim_views, float *__restrict__ vw, float *__restrict__ agg, int B,
-                           int D, size_t HW, int n_src, const __grid_constant__ PwnParams prm)
+// PixelwiseNet (eval, BatchNorm folded): one thread per (view, pixel) sweeps the D similarities through the
+// 1 -> 16 -> 8 -> 1 MLP and keeps the maximum logit (sigmoid is monotone: one sigmoid per thread).  The weighted
+// aggregation is then the ordinary aggregate_fwd_kernel, which re-reads the similarities from L2.
+__global__ void __launch_bounds__(256, 4)
+pixelwise_weight_kernel(const float *__restrict__ sim_views, float *__restrict__ vw, int B, int D, size_t HW, int n_src,
+                        const __grid_constant__ PwnParams prm)
 {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
-    const int b = blockIdx.y;
-    float acc[DT];
+    const int i = blockIdx.y, b = blockIdx.z;
+    const float *sv = sim_views + (((size_t)i * B + b) * D) * HW + p;
+    float best = -INFINITY;
+#pragma unroll 2
+    for (int d = 0; d < D; ++d) {
+        const float x = __ldg(sv + (size_t)d * HW);
+        float h0[16];
 #pragma unroll
-    for (int d = 0; d < DT; ++d) acc[d] = 0.0f;
-    float wsum = 1e-5f;
-    for (int i = 0; i < n_src; ++i) {
-        const float *sv = sim_views + (((size_t)i * B + b) * D) * HW + p;
-        float best = -INFINITY;
-        for (int d = 0; d < D; ++d) {
-            const float x = __ldg(sv + (size_t)d * HW);
-            float h0[16];
+        for (int c = 0; c < 16; ++c) h0[c] = fmaxf(fmaf(prm.w0[c], x, prm.b0[c]), 0.0f);
+        float o = prm.b2;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) h0[c] = fmaxf(fmaf(prm.w0[c], x, prm.b0[c]), 0.0f);
-            float o = prm.b2;
+        for (int j = 0; j < 8; ++j) {
+            float h = prm.b1[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float h = prm.b1[j];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) h = fmaf(prm.w1[j][c], h0[c], h);
-                o = fmaf(prm.w2[j], fmaxf(h, 0.0f), o);
-            }
-            best = fmaxf(best, o);
+            for (int c = 0; c < 16; ++c) h = fmaf(prm.w1[j][c], h0[c], h);
+            o = fmaf(prm.w2[j], fmaxf(h, 0.0f), o);
         }
-        const float w = 1.0f / (1.0f + expf(-best));            // nn.Sigmoid, then max over D (TransMVSNet.py:26-28)
-        vw[((size_t)b * n_src + i) * HW + p] = w;
-#pragma unroll
-        for (int d = 0; d < DT; ++d)
-            if (d < D) acc[d] = __fadd_rn(acc[d], __fmul_rn(__ldg(sv + (size_t)d * HW), w));
-        wsum = __fadd_rn(wsum, w);
+        best = fmaxf(best, o);
     }
-#pragma unroll
-    for (int d = 0; d < DT; ++d)
-        if (d < D) __stcs(agg + ((size_t)b * D + d) * HW + p, __fdiv_rn(acc[d], wsum));
+    vw[((size_t)b * n_src + i) * HW + p] = 1.0f / (1.0f + expf(-best));     // nn.Sigmoid, max over D (TransMVSNet.py:26-28)
 }
 
 }  // namespace
@@ -264,17 +250,16 @@ extern "C" int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float 
 {
     if (!sim_views || !mlp || !view_weights || !agg) return TMVS_E_NULL;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0 || B > 65535) return TMVS_E_SHAPE;
-    if (D > 64) return TMVS_E_UNSUPPORTED;          // accumulators live in registers
+    if (n_src > 65535) return TMVS_E_SHAPE;
     PwnParams prm;
     memcpy(&prm, mlp, sizeof(float) * TMVS_PWN_PARAMS);
     const size_t HW = (size_t)H * W;
-    dim3 grid((unsigned)((HW + 127) / 128), B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (D <= 8) pixelwise_aggregate_kernel<8><<<grid, 128, 0, st>>>(sim_views, view_weights, agg, B, D, HW, n_src, prm);
-    else if (D <= 32) pixelwise_aggregate_kernel<32><<<grid, 128, 0, st>>>(sim_views, view_weights, agg, B, D, HW, n_src, prm);
-    else if (D <= 48) pixelwise_aggregate_kernel<48><<<grid, 128, 0, st>>>(sim_views, view_weights, agg, B, D, HW, n_src, prm);
-    else pixelwise_aggregate_kernel<64><<<grid, 128, 0, st>>>(sim_views, view_weights, agg, B, D, HW, n_src, prm);
-    return tmvs_launch_status();
+    pixelwise_weight_kernel<<<dim3((unsigned)((HW + 255) / 256), n_src, B), 256, 0, st>>>(sim_views, view_weights, B, D,
+                                                                                          HW, n_src, prm);
+    int rc = tmvs_launch_status();
+    if (rc != TMVS_OK) return rc;
+    return tmvs_aggregate_fwd(sim_views, view_weights, agg, B, D, H, W, n_src, stream);
 }
 
 extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,

@@ -54,6 +54,16 @@ class DepthNet(nn.Module):
     def __init__(self):
         super().__init__()
         self.pixel_wise_net = PixelwiseNet()
+        self._fold_key = None
+        self._fold = None
+
+    def _folded_mlp(self) -> torch.Tensor:
+        """BatchNorm-folded PixelwiseNet parameters, recomputed only when a parameter or buffer changed."""
+        tensors = list(self.pixel_wise_net.parameters()) + list(self.pixel_wise_net.buffers())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self._fold_key:
+            self._fold, self._fold_key = ops.fold_pixelwise_net(self.pixel_wise_net), key
+        return self._fold
 
     def forward(self, features, proj_matrix, depth_values, num_depth, cost_regularization, view_weights=None):
         """Same contract as models/TransMVSNet.py:38-109.
@@ -69,10 +79,10 @@ class DepthNet(nn.Module):
         learned = view_weights is None
         if learned:
             _, sim_views = ops.cost_volume(ref_feature, src_features, rot_trans, depth_values, None, True)
-            folded = (not self.training) and (not torch.is_grad_enabled()) and num_depth <= 64
+            folded = (not self.training) and (not torch.is_grad_enabled())
             if folded:
                 # inference: PixelwiseNet (BatchNorm folded) + aggregation in one kernel
-                view_weights, similarity = ops.pixelwise_aggregate(sim_views, ops.fold_pixelwise_net(self.pixel_wise_net))
+                view_weights, similarity = ops.pixelwise_aggregate(sim_views, self._folded_mlp())
             else:
                 weights = [self.pixel_wise_net(sim_views[i].unsqueeze(1)) for i in range(sim_views.shape[0])]
                 view_weights = torch.cat(weights, dim=1)                   # [B,Nsrc,H,W]
