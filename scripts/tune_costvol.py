@@ -42,7 +42,7 @@ def time_variant(lib_path, dev_stages, reps=10):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     _lib._LIB = lib
-    out = []
+    out, outs = [], []
     for d in dev_stages:
         packed = ops.pack_sources(d["features"][1:])
         run = lambda: ops.cost_volume_packed(d["features"][0], packed, d["rot_trans"], d["depth_values"],
@@ -56,7 +56,8 @@ def time_variant(lib_path, dev_stages, reps=10):
         e1.record()
         torch.cuda.synchronize()
         out.append(e0.elapsed_time(e1) / reps)
-    return out
+        outs.append(run()[0])
+    return out, outs
 
 
 def main():
@@ -68,18 +69,21 @@ def main():
     for ty, dc, unroll in itertools.product((8, 4), (8, 16), (1, 2)):
         for mb in ((2, 3, 4), (2, 2, 3), (2, 2, 2), (2, 4, 5)):
             grid.append(dict(TMVS_TILE_Y=ty, TMVS_DC=dc, TMVS_UNROLL=unroll, TMVS_MINB8=mb[0], TMVS_MINB4=mb[1], TMVS_MINB2=mb[2]))
-    if len(sys.argv) > 1:       # explicit list: '[{"TMVS_DOT_CACHE":0}, ...]' merged over the defaults
+    if len(sys.argv) > 1:       # explicit list: '[{"TMVS_FWD_V":3}, ...]' merged over the defaults
         import json
-        base = dict(TMVS_TILE_Y=8, TMVS_DC=8, TMVS_UNROLL=2, TMVS_MINB8=2, TMVS_MINB4=4, TMVS_MINB2=5, TMVS_DOT_CACHE=1)
+        base = dict(TMVS_TILE_Y=8, TMVS_DC=8, TMVS_UNROLL=2, TMVS_MINB8=2, TMVS_MINB4=4, TMVS_MINB2=5, TMVS_FWD_V=4, TMVS_FFMA2=1)
         grid = [{**base, **g} for g in json.loads(sys.argv[1])]
-    print("tile_y dc unroll minb(8/4/2)    s1_ms   s2_ms   s3_ms   sum", flush=True)
+    print("variant                                          s1_ms   s2_ms   s3_ms   sum   | max rel diff vs first variant", flush=True)
+    first = None
     for i, defs in enumerate(grid):
         try:
             lib = build_variant(f"v{i}", defs)
-            t = time_variant(lib, dev_stages)
-            print(f"cache={defs.get('TMVS_DOT_CACHE', 1)} {defs['TMVS_TILE_Y']:6d} {defs['TMVS_DC']:2d} {defs['TMVS_UNROLL']:6d} "
-                  f"{defs['TMVS_MINB8']}/{defs['TMVS_MINB4']}/{defs['TMVS_MINB2']}         "
-                  f"{t[0]:7.4f} {t[1]:7.4f} {t[2]:7.4f} {sum(t):7.4f}", flush=True)
+            t, outs = time_variant(lib, dev_stages)
+            if first is None:
+                first = outs
+            diff = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(outs, first)]
+            tag = " ".join(f"{k[5:]}={v}" for k, v in defs.items())
+            print(f"{tag:48s} {t[0]:7.4f} {t[1]:7.4f} {t[2]:7.4f} {sum(t):7.4f} | " + " ".join(f"{d:.1e}" for d in diff), flush=True)
         except subprocess.CalledProcessError as e:
             print("build failed", defs, e.stderr[-300:] if e.stderr else "", flush=True)
 

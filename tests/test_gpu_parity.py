@@ -100,10 +100,12 @@ def test_cost_volume_full_size_stage3_vs_oracle():
     assert_costvol_close(agg.cpu().numpy(), o_agg, "full-size stage 3")
 
 
-def test_tma_and_l1_paths_agree_bitwise(monkeypatch):
-    """The TMA-staged shared-memory kernel and the L1 global-gather kernel do the same arithmetic in the same
-    order: identical bits, for a cascade-shaped case, a tiny image (box larger than the image) and a case whose
-    window does not fit any box (6x zoom-in -> global path inside the TMA kernel)."""
+def test_tma_and_l1_paths_agree(monkeypatch):
+    """The TMA-staged shared-memory kernel and the L1 global-gather kernel land on the same sample positions and
+    weights (same coordinate arithmetic); only the order of the channel sum differs (the L1 kernel accumulates even
+    and odd channels separately for FFMA2), so they agree to fp32 re-association: <= 2e-6 of the volume's range.
+    Cases: cascade shapes, a tiny image (box larger than the image) and a case whose window does not fit any box
+    (6x zoom-in -> global path inside the TMA kernel)."""
     cases = []
     for stage, hw in ((1, (160, 224)), (2, (96, 136)), (3, (48, 72)), (3, (8, 8))):
         st = synthetic.make_stage(stage, batch=2, n_views=4, height=hw[0], width=hw[1], seed=13)
@@ -119,7 +121,8 @@ def test_tma_and_l1_paths_agree_bitwise(monkeypatch):
         agg_t, views_t = tm.cost_volume(*args, want_views=True)
         monkeypatch.delenv("TMVS_COSTVOL_PATH", raising=False)
         agg_l, views_l = tm.cost_volume(*args, want_views=True)
-        assert torch.equal(agg_t, agg_l) and torch.equal(views_t, views_l)
+        for a, b in ((agg_t, agg_l), (views_t, views_l)):
+            assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
         _, o_agg = oracle.costvol_fwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values,
                                       st.view_weights, want_views=False)
         assert_costvol_close(agg_t.cpu().numpy(), o_agg, "tma path vs oracle")

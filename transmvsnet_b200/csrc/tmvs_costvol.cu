@@ -51,13 +51,174 @@ constexpr int kDC = TMVS_DC;      // depth planes per thread
 // registers -> resident CTAs per SM: the C=32 kernel needs ~128 registers (2 CTAs), the smaller ones fit 3-4
 template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? TMVS_MINB8 : (C4T >= 4 ? TMVS_MINB4 : TMVS_MINB2); };
 
-template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG>
+#ifndef TMVS_FWD_V
+#define TMVS_FWD_V 4
+#endif
+#ifndef TMVS_FFMA2
+#define TMVS_FFMA2 1
+#endif
+
+#if TMVS_FWD_V == 4
+// One thread = one reference pixel x kDC depth planes, looping views outside and planes inside.
+// Per plane: the reference's coordinate arithmetic (tmvs_coords_lean), one footprint, 4*C4 128-bit loads from the
+// packed source and 4 channel dot products against the register-resident reference vector (FFMA2: two fp32 FMAs
+// per issue slot), then 4 bilinear weights.  Footprints that lie wholly inside the source image (all but a rim of
+// warps) skip every clamp, bounds predicate and select; the rim takes the general branch below.
+template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG, bool RECIP>
 __global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value * (8 / TMVS_TILE_Y))
 costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
                    const float4 *__restrict__ packed, const float *__restrict__ depth,
                    const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
                    int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
-                   int n_dchunks, const __grid_constant__ TmvsGeom geom)
+                   int n_dchunks, const __grid_constant__ TmvsFwdConst kc, const __grid_constant__ TmvsGeom geom)
+{
+    // the depth chunk is the FASTEST block index: the CTAs that sweep the same source neighbourhood for
+    // different depth planes are co-scheduled, so each source line comes from HBM once and from L2 after
+    __shared__ float acc_s[AGG ? kDC : 1][kTileX * kTileY];
+    const int chunk = blockIdx.x % n_dchunks;
+    const int x = (blockIdx.x / n_dchunks) * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int tid = threadIdx.y * kTileX + threadIdx.x;
+    const int bl = blockIdx.z;                        // batch item within this launch
+    const int d0 = chunk * kDC;
+    const int nd = min(kDC, D - d0);
+    const int b = b_first + bl;
+    const int HW = H * W;
+    const int pix = y * W + x;
+
+    // reference channels -> registers as (even, odd) pairs, the operand shape of FFMA2
+    float2 r[2 * C4T];
+    {
+        const float *rp = ref + b * rB + y * rH + x * rW;
+#pragma unroll
+        for (int g = 0; g < 2 * C4T; ++g) {
+            const int c = 2 * g;
+            r[g].x = (c < C) ? __ldg(rp + c * rC) : 0.0f;
+            r[g].y = (c + 1 < C) ? __ldg(rp + (c + 1) * rC) : 0.0f;
+        }
+    }
+    const float *dep_base = PER_PIXEL ? depth + ((size_t)b * D + d0) * HW + pix : depth + (size_t)b * D + d0;
+    const int dep_stride = PER_PIXEL ? kc.hw : 1;
+    if (AGG) {
+#pragma unroll
+        for (int k = 0; k < kDC; ++k) acc_s[k][tid] = 0.0f;
+    }
+    float wsum = 1e-5f;                                // TransMVSNet.py:72
+    const unsigned c4x8 = EXACT ? C4T * 8 : c4 * 8;
+    const size_t slice = (size_t)H * kc.row;
+    const float xf = (float)x, yf = (float)y;
+
+    for (int i = 0; i < n_src; ++i) {
+        const float *rt = geom.rt[i * b_chunk + bl];
+        const TmvsRay ray = tmvs_ray(rt, xf, yf);
+        float tx = rt[9], ty = rt[10], tz = rt[11];
+        // opaque to the optimiser: keep them in registers for the depth loop instead of re-deriving them (constant-bank
+        // index arithmetic and 64-bit multiplies) once per plane
+        asm volatile("" : "+f"(tx), "+f"(ty), "+f"(tz));
+        float wi = 0.0f;
+        if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
+        const float4 *img = packed + ((size_t)i * b_total + b) * slice;
+        asm volatile("" : "+l"(img));
+        float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
+        const float *dep_p = dep_base;
+        TMVS_PRAGMA(unroll TMVS_UNROLL)
+        for (int k = 0; k < nd; ++k, dep_p += dep_stride, out_v += kc.hw) {
+            const float2 pos = tmvs_coords_lean<RECIP>(ray.rx, ray.ry, ray.rz, tx, ty, tz, __ldg(dep_p), kc);
+            // ATen grid_sampler_2d corner weights (nw, ne, sw, se)
+            const float fx0 = floorf(pos.x), fy0 = floorf(pos.y);
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            float ax = __fsub_rn(fx0 + 1.0f, pos.x), bx = __fsub_rn(pos.x, fx0);
+            float ay = __fsub_rn(fy0 + 1.0f, pos.y), by = __fsub_rn(pos.y, fy0);
+            unsigned o00, o01, o10, o11;
+            bool any = true;
+            if ((unsigned)x0 < (unsigned)kc.wm1 && (unsigned)y0 < (unsigned)kc.hm1) {
+                // whole footprint in bounds: one offset, three increments
+                const unsigned dx = ((x0 & 7) == 7) ? c4x8 - 7u : 1u;
+                o00 = (unsigned)y0 * (unsigned)kc.row + ((unsigned)x0 >> 3) * c4x8 + ((unsigned)x0 & 7u);
+                o01 = o00 + dx;
+                o10 = o00 + (unsigned)kc.row;
+                o11 = o10 + dx;
+            } else {
+                // rim: per-tap zero padding -- an out-of-bounds tap gets weight 0 and a clamped (valid) address
+                const bool xin0 = (unsigned)x0 <= (unsigned)kc.wm1, xin1 = (unsigned)(x0 + 1) <= (unsigned)kc.wm1;
+                const bool yin0 = (unsigned)y0 <= (unsigned)kc.hm1, yin1 = (unsigned)(y0 + 1) <= (unsigned)kc.hm1;
+                any = (xin0 | xin1) & (yin0 | yin1);
+                ax = xin0 ? ax : 0.0f; bx = xin1 ? bx : 0.0f;
+                ay = yin0 ? ay : 0.0f; by = yin1 ? by : 0.0f;
+                const unsigned xa = (unsigned)min(max(x0, 0), kc.wm1), xb = (unsigned)min(max(x0 + 1, 0), kc.wm1);
+                const unsigned ra = (unsigned)min(max(y0, 0), kc.hm1) * (unsigned)kc.row;
+                const unsigned rb = (unsigned)min(max(y0 + 1, 0), kc.hm1) * (unsigned)kc.row;
+                const unsigned oa = (xa >> 3) * c4x8 + (xa & 7u), ob = (xb >> 3) * c4x8 + (xb & 7u);
+                o00 = ra + oa; o01 = ra + ob; o10 = rb + oa; o11 = rb + ob;
+            }
+            float s = 0.0f;
+            if (any) {
+                const float4 *p00 = tmvs_pk_ptr(img, o00);
+                const float4 *p01 = tmvs_pk_ptr(img, o01);
+                const float4 *p10 = tmvs_pk_ptr(img, o10);
+                const float4 *p11 = tmvs_pk_ptr(img, o11);
+#if TMVS_FFMA2
+                float2 s00 = make_float2(0.f, 0.f), s01 = s00, s10 = s00, s11 = s00;
+#pragma unroll
+                for (int g = 0; g < C4T; ++g) {
+                    if (EXACT || g < c4) {
+                        const float4 a = ldg4(p00 + g * 8);        // + g * 128 bytes: an immediate
+                        const float4 bq = ldg4(p01 + g * 8);
+                        const float4 cq = ldg4(p10 + g * 8);
+                        const float4 dq = ldg4(p11 + g * 8);
+                        s00 = tmvs_fma2(make_float2(a.x, a.y), r[2 * g], s00);
+                        s01 = tmvs_fma2(make_float2(bq.x, bq.y), r[2 * g], s01);
+                        s10 = tmvs_fma2(make_float2(cq.x, cq.y), r[2 * g], s10);
+                        s11 = tmvs_fma2(make_float2(dq.x, dq.y), r[2 * g], s11);
+                        s00 = tmvs_fma2(make_float2(a.z, a.w), r[2 * g + 1], s00);
+                        s01 = tmvs_fma2(make_float2(bq.z, bq.w), r[2 * g + 1], s01);
+                        s10 = tmvs_fma2(make_float2(cq.z, cq.w), r[2 * g + 1], s10);
+                        s11 = tmvs_fma2(make_float2(dq.z, dq.w), r[2 * g + 1], s11);
+                    }
+                }
+                const float t00 = s00.x + s00.y, t01 = s01.x + s01.y, t10 = s10.x + s10.y, t11 = s11.x + s11.y;
+#else
+                float t00 = 0.0f, t01 = 0.0f, t10 = 0.0f, t11 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < C4T; ++g) {
+                    if (EXACT || g < c4) {
+                        const float4 a = ldg4(p00 + g * 8);
+                        const float4 bq = ldg4(p01 + g * 8);
+                        const float4 cq = ldg4(p10 + g * 8);
+                        const float4 dq = ldg4(p11 + g * 8);
+                        const float4 rr = make_float4(r[2 * g].x, r[2 * g].y, r[2 * g + 1].x, r[2 * g + 1].y);
+                        t00 = dot4(rr, a, t00);
+                        t01 = dot4(rr, bq, t01);
+                        t10 = dot4(rr, cq, t10);
+                        t11 = dot4(rr, dq, t11);
+                    }
+                }
+#endif
+                s = __fmul_rn(ax, ay) * t00;
+                s = fmaf(__fmul_rn(bx, ay), t01, s);
+                s = fmaf(__fmul_rn(ax, by), t10, s);
+                s = fmaf(__fmul_rn(bx, by), t11, s);
+                s *= kc.inv_c;                            // .mean(1), TransMVSNet.py:80
+            }
+            if (VIEWS) __stcs(out_v, s);
+            if (AGG) acc_s[k][tid] = __fadd_rn(acc_s[k][tid], __fmul_rn(s, wi));   // TransMVSNet.py:88
+        }
+        wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
+    }
+    if (AGG) {
+        float *out_a = agg + ((size_t)b * D + d0) * HW + pix;
+        for (int k = 0; k < nd; ++k) __stcs(out_a + (size_t)k * HW, __fdiv_rn(acc_s[k][tid], wsum));   // :93
+    }
+}
+#else   // TMVS_FWD_V == 3: the previous kernel, kept for A/B timing (scripts/tune_costvol.py)
+template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG, bool RECIP>
+__global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value * (8 / TMVS_TILE_Y))
+costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                   const float4 *__restrict__ packed, const float *__restrict__ depth,
+                   const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
+                   int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
+                   int n_dchunks, const __grid_constant__ TmvsFwdConst kc, const __grid_constant__ TmvsGeom geom)
 {
     // the depth chunk is the FASTEST block index: the CTAs that sweep the same source neighbourhood for
     // different depth planes are co-scheduled, so each source line comes from HBM once and from L2 after
@@ -152,16 +313,19 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     }
 }
 
-template <int C4T, bool EXACT, bool PER_PIXEL>
+#endif
+
+template <int C4T, bool EXACT, bool PER_PIXEL, bool RECIP>
 int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
                 const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float4 *packed,
                 const float *depth, const float *vw, float *sim_views, float *agg, int b_total, int b_first,
-                int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsGeom &geom)
+                int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsFwdConst &kc,
+                const TmvsGeom &geom)
 {
 #define TMVS_LAUNCH(V, A)                                                                                 \
-    costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A><<<grid, block, 0, st>>>(                              \
+    costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP><<<grid, block, 0, st>>>(                              \
         ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,  \
-        W, n_src, n_dchunks, geom)
+        W, n_src, n_dchunks, kc, geom)
     if (views && do_agg) TMVS_LAUNCH(true, true);
     else if (views) TMVS_LAUNCH(true, false);
     else TMVS_LAUNCH(false, true);
@@ -169,25 +333,25 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
     return tmvs_launch_status();
 }
 
-template <bool PER_PIXEL, typename... Args>
+template <bool PER_PIXEL, bool RECIP, typename... Args>
 int launch_c4(int c4, Args... args)
 {
 #ifdef TMVS_FAST_BUILD      // tuning builds: only the three exact kernels
     switch (c4) {
-    case 2: return launch_mode<2, true, PER_PIXEL>(args...);
-    case 4: return launch_mode<4, true, PER_PIXEL>(args...);
-    default: return launch_mode<8, true, PER_PIXEL>(args...);
+    case 2: return launch_mode<2, true, PER_PIXEL, RECIP>(args...);
+    case 4: return launch_mode<4, true, PER_PIXEL, RECIP>(args...);
+    default: return launch_mode<8, true, PER_PIXEL, RECIP>(args...);
     }
 #else
     switch (c4) {
-    case 2: return launch_mode<2, true, PER_PIXEL>(args...);
-    case 4: return launch_mode<4, true, PER_PIXEL>(args...);
-    case 8: return launch_mode<8, true, PER_PIXEL>(args...);
+    case 2: return launch_mode<2, true, PER_PIXEL, RECIP>(args...);
+    case 4: return launch_mode<4, true, PER_PIXEL, RECIP>(args...);
+    case 8: return launch_mode<8, true, PER_PIXEL, RECIP>(args...);
     default: break;
     }
-    if (c4 <= 4) return launch_mode<4, false, PER_PIXEL>(args...);
-    if (c4 <= 8) return launch_mode<8, false, PER_PIXEL>(args...);
-    return launch_mode<16, false, PER_PIXEL>(args...);
+    if (c4 <= 4) return launch_mode<4, false, PER_PIXEL, RECIP>(args...);
+    if (c4 <= 8) return launch_mode<8, false, PER_PIXEL, RECIP>(args...);
+    return launch_mode<16, false, PER_PIXEL, RECIP>(args...);
 #endif
 }
 
@@ -290,6 +454,8 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
         if (rc != TMVS_E_UNSUPPORTED) return rc;
     }
     dim3 block(kTileX, kTileY);
+    const TmvsFwdConst kc = tmvs_fwd_const(C, c4, H, W);
+    const bool recip = tmvs_arith_mode() == TMVS_ARITH_ATEN_CUDA;
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
@@ -300,14 +466,14 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
                     geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
         dim3 grid(((W + kTileX - 1) / kTileX) * n_dchunks, (H + kTileY - 1) / kTileY, bc);
         int rc;
+#define TMVS_FWD_ARGS c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,                   \
+                      (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D, H, W, n_src,      \
+                      n_dchunks, kc, geom
         if (per_pixel)
-            rc = launch_c4<true>(c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,
-                                 (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D,
-                                 H, W, n_src, n_dchunks, geom);
+            rc = recip ? launch_c4<true, true>(TMVS_FWD_ARGS) : launch_c4<true, false>(TMVS_FWD_ARGS);
         else
-            rc = launch_c4<false>(c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,
-                                  (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D,
-                                  H, W, n_src, n_dchunks, geom);
+            rc = recip ? launch_c4<false, true>(TMVS_FWD_ARGS) : launch_c4<false, false>(TMVS_FWD_ARGS);
+#undef TMVS_FWD_ARGS
         if (rc != TMVS_OK) return rc;
     }
     return TMVS_OK;
