@@ -267,10 +267,24 @@ def run_tmvs_arm(args, workload):
     tr_path = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tr_path):
         traffic = json.load(open(tr_path)).get(top["kernel"])
+    # The fused cost-volume kernel is bound by the SM's load data path, not HBM: every voxel-view
+    # moves 4 taps x C channels x 4 bytes from L1 into registers.  Peak = LDG.128 from L1-resident data on all SMs,
+    # measured on this GPU pool by scripts/l1_peak.cu (profiles/r1_l1_peak.json); reported beside the HBM fraction.
+    sm_load = None
+    l1_path = os.path.join(REPO, "profiles", "r1_l1_peak.json")
+    if top["kernel"].startswith("costvol_fwd") and os.path.exists(l1_path):
+        l1_peak = [t for t in json.load(open(l1_path))["tests"] if t["name"] == "ldg128_aligned"][0]["GBps"]
+        st = host[int(top["kernel"][-1]) - 1]
+        tap_bytes = 16.0 * st.features[0].shape[1] * st.voxel_views
+        l1_gbps = tap_bytes / 1e9 / (top["ms"] * 1e-3)
+        sm_load = {"what": "bilinear-tap bytes delivered from L1 to registers (4 taps x C x 4 B per voxel-view)",
+                   "bytes": int(tap_bytes), "achieved": round(l1_gbps, 1), "peak": l1_peak, "unit": "GB/s",
+                   "frac": round(l1_gbps / l1_peak, 4),
+                   "peak_source": "profiles/r1_l1_peak.json ldg128_aligned (scripts/l1_peak.cu, B200, 148 SMs)"}
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbps"], "peak": peak, "unit": "GB/s",
                 "frac": round(top["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": top["ms"], "algorithmic_bytes": int(top["algorithmic_mb"] * 1e6),
-                "all_kernels": kernels,
+                "all_kernels": kernels, "sm_load_path": sm_load,
                 "step_algorithmic_frac": round(sum(k["algorithmic_mb"] for k in kernels) * 1e6 / 1e9 /
                                                (elapsed_ms * 1e-3 / args.steps) / peak, 4)}
 

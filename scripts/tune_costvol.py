@@ -71,7 +71,7 @@ def main():
             grid.append(dict(TMVS_TILE_Y=ty, TMVS_DC=dc, TMVS_UNROLL=unroll, TMVS_MINB8=mb[0], TMVS_MINB4=mb[1], TMVS_MINB2=mb[2]))
     if len(sys.argv) > 1:       # explicit list: '[{"TMVS_FWD_V":3}, ...]' merged over the defaults
         import json
-        base = dict(TMVS_TILE_Y=8, TMVS_DC=8, TMVS_UNROLL=2, TMVS_MINB8=2, TMVS_MINB4=4, TMVS_MINB2=5, TMVS_FWD_V=4, TMVS_FFMA2=1)
+        base = dict(TMVS_TILE_Y=8, TMVS_DC=8, TMVS_UNROLL=2, TMVS_MINB8=2, TMVS_MINB4=4, TMVS_MINB2=5, TMVS_FFMA2=1)
         grid = [{**base, **g} for g in json.loads(sys.argv[1])]
     print("variant                                          s1_ms   s2_ms   s3_ms   sum   | max rel diff vs first variant", flush=True)
     first = None

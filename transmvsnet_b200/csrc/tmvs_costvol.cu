@@ -51,14 +51,10 @@ constexpr int kDC = TMVS_DC;      // depth planes per thread
 // registers -> resident CTAs per SM: the C=32 kernel needs ~128 registers (2 CTAs), the smaller ones fit 3-4
 template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? TMVS_MINB8 : (C4T >= 4 ? TMVS_MINB4 : TMVS_MINB2); };
 
-#ifndef TMVS_FWD_V
-#define TMVS_FWD_V 4
-#endif
 #ifndef TMVS_FFMA2
 #define TMVS_FFMA2 1
 #endif
 
-#if TMVS_FWD_V == 4
 // One thread = one reference pixel x kDC depth planes, looping views outside and planes inside.
 // Per plane: the reference's coordinate arithmetic (tmvs_coords_lean), one footprint, 4*C4 128-bit loads from the
 // packed source and 4 channel dot products against the register-resident reference vector (FFMA2: two fp32 FMAs
@@ -211,110 +207,6 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
         for (int k = 0; k < nd; ++k) __stcs(out_a + (size_t)k * HW, __fdiv_rn(acc_s[k][tid], wsum));   // :93
     }
 }
-#else   // TMVS_FWD_V == 3: the previous kernel, kept for A/B timing (scripts/tune_costvol.py)
-template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG, bool RECIP>
-__global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value * (8 / TMVS_TILE_Y))
-costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
-                   const float4 *__restrict__ packed, const float *__restrict__ depth,
-                   const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
-                   int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
-                   int n_dchunks, const __grid_constant__ TmvsFwdConst kc, const __grid_constant__ TmvsGeom geom)
-{
-    // the depth chunk is the FASTEST block index: the CTAs that sweep the same source neighbourhood for
-    // different depth planes are co-scheduled, so each source line comes from HBM once and from L2 after
-    __shared__ float acc_s[AGG ? kDC : 1][kTileX * kTileY];
-    const int chunk = blockIdx.x % n_dchunks;
-    const int x = (blockIdx.x / n_dchunks) * kTileX + threadIdx.x;
-    const int y = blockIdx.y * kTileY + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int tid = threadIdx.y * kTileX + threadIdx.x;
-    const int bl = blockIdx.z;                        // batch item within this launch
-    const int d0 = chunk * kDC;
-    const int nd = min(kDC, D - d0);
-    const int b = b_first + bl;
-    const int HW = H * W;
-    const int pix = y * W + x;
-
-    // reference channels -> registers (coalesced per channel for NCHW)
-    float4 r[C4T];
-    {
-        const float *rp = ref + b * rB + y * rH + x * rW;
-#pragma unroll
-        for (int g = 0; g < C4T; ++g) {
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int c = 4 * g + j;
-                v[j] = (c < C) ? __ldg(rp + c * rC) : 0.0f;
-            }
-            r[g] = make_float4(v[0], v[1], v[2], v[3]);
-        }
-    }
-    const float *dep_base = PER_PIXEL ? depth + ((size_t)b * D + d0) * HW + pix : depth + (size_t)b * D + d0;
-    const int dep_stride = PER_PIXEL ? HW : 1;
-    if (AGG) {
-#pragma unroll
-        for (int k = 0; k < kDC; ++k) acc_s[k][tid] = 0.0f;
-    }
-    float wsum = 1e-5f;                                // TransMVSNet.py:72
-    const float inv_c = 1.0f / (float)C;
-    const TmvsDims dims = tmvs_dims(H, W, geom.arith);
-    const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
-    const float xf = (float)x, yf = (float)y;
-
-    for (int i = 0; i < n_src; ++i) {
-        const float *rt = geom.rt[i * b_chunk + bl];
-        const TmvsRay ray = tmvs_ray(rt, xf, yf);
-        float wi = 0.0f;
-        if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
-        const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;
-        float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
-        const float *dep_p = dep_base;
-        TMVS_PRAGMA(unroll TMVS_UNROLL)
-        for (int k = 0; k < nd; ++k, dep_p += dep_stride, out_v += HW) {
-            const TmvsTaps t = tmvs_taps(ray, rt, __ldg(dep_p), dims);
-            float s = 0.0f;
-            if (t.any) {
-                const int xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-                const int ra = min(max(t.y0, 0), H - 1) * pk.row, rb = min(max(t.y0 + 1, 0), H - 1) * pk.row;
-                const float4 *p00 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, ra));
-                const float4 *p01 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, ra));
-                const float4 *p10 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xa, rb));
-                const float4 *p11 = tmvs_pk_ptr(img, tmvs_pk_off(pk, xb, rb));
-                float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
-#pragma unroll
-                for (int g = 0; g < C4T; ++g) {
-                    if (EXACT || g < c4) {
-                        const float4 a = ldg4(p00 + g * 8);        // + g * 128 bytes: an immediate
-                        const float4 bq = ldg4(p01 + g * 8);
-                        const float4 cq = ldg4(p10 + g * 8);
-                        const float4 dq = ldg4(p11 + g * 8);
-                        s00 = dot4(r[g], a, s00);
-                        s01 = dot4(r[g], bq, s01);
-                        s10 = dot4(r[g], cq, s10);
-                        s11 = dot4(r[g], dq, s11);
-                    }
-                }
-                // per-tap zero padding: an out-of-bounds tap contributes nothing
-                s = t.ok00 ? t.w00 * s00 : 0.0f;
-                s += t.ok01 ? t.w01 * s01 : 0.0f;
-                s += t.ok10 ? t.w10 * s10 : 0.0f;
-                s += t.ok11 ? t.w11 * s11 : 0.0f;
-                s *= inv_c;                               // .mean(1), TransMVSNet.py:80
-            }
-            if (VIEWS) __stcs(out_v, s);
-            if (AGG) acc_s[k][tid] = __fadd_rn(acc_s[k][tid], __fmul_rn(s, wi));   // TransMVSNet.py:88
-        }
-        wsum = __fadd_rn(wsum, wi);                                       // TransMVSNet.py:89
-    }
-    if (AGG) {
-        float *out_a = agg + ((size_t)b * D + d0) * HW + pix;
-        for (int k = 0; k < nd; ++k) __stcs(out_a + (size_t)k * HW, __fdiv_rn(acc_s[k][tid], wsum));   // :93
-    }
-}
-
-#endif
-
 template <int C4T, bool EXACT, bool PER_PIXEL, bool RECIP>
 int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
                 const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float4 *packed,
@@ -322,13 +214,13 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
                 int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsFwdConst &kc,
                 const TmvsGeom &geom)
 {
-#define TMVS_LAUNCH(V, A)                                                                                 \
-    costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP><<<grid, block, 0, st>>>(                              \
-        ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,  \
+#define TMVS_LAUNCH(V, A)                                                                                    \
+    costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP><<<grid, block, 0, st>>>(                          \
+        ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,      \
         W, n_src, n_dchunks, kc, geom)
-    if (views && do_agg) TMVS_LAUNCH(true, true);
-    else if (views) TMVS_LAUNCH(true, false);
-    else TMVS_LAUNCH(false, true);
+    if (views && do_agg) { TMVS_LAUNCH(true, true); }
+    else if (views) { TMVS_LAUNCH(true, false); }
+    else { TMVS_LAUNCH(false, true); }
 #undef TMVS_LAUNCH
     return tmvs_launch_status();
 }
