@@ -1,4 +1,4 @@
-"""Rebuild tmvs_costvol_bwd.cu with different tunables and time grad_src at the DTU stage sizes (GPU box)."""
+"""Rebuild tmvs_costvol_bwd.cu / tmvs_costvol_bwd_cells.cu with different tunables and time grad_src at the DTU stage sizes (GPU box)."""
 import ctypes, json, os, subprocess, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 flags0 = [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
 objs = {}
 for src in build.SOURCES:
-    if src != "tmvs_costvol_bwd.cu":
+    if src not in ("tmvs_costvol_bwd.cu", "tmvs_costvol_bwd_cells.cu"):
         o = os.path.join(SCRATCH, src + ".o")
         subprocess.run(["nvcc", *flags0, "-c", os.path.join(CSRC, src), "-o", o], check=True, capture_output=True)
         objs[src] = o
@@ -22,11 +22,13 @@ for stage in (1, 2, 3):
     cases.append((st, rt))
 for defs in json.loads(sys.argv[1]):
     o = os.path.join(SCRATCH, "bwd.o")
+    o2 = os.path.join(SCRATCH, "bwd_cells.o")
     r = subprocess.run(["nvcc", *flags0, *[f"-D{k}={v}" for k, v in defs.items()], "-c", os.path.join(CSRC, "tmvs_costvol_bwd.cu"), "-o", o], capture_output=True, text=True)
-    if r.returncode:
-        print(defs, "build failed", r.stderr[-200:]); continue
+    r2 = subprocess.run(["nvcc", *flags0, *[f"-D{k}={v}" for k, v in defs.items()], "-c", os.path.join(CSRC, "tmvs_costvol_bwd_cells.cu"), "-o", o2], capture_output=True, text=True)
+    if r.returncode or r2.returncode:
+        print(defs, "build failed", r.stderr[-200:], r2.stderr[-200:]); continue
     lib = os.path.join(SCRATCH, "lib.so")
-    subprocess.run(["nvcc", "-shared", "-o", lib, *objs.values(), o, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
+    subprocess.run(["nvcc", "-shared", "-o", lib, *objs.values(), o, o2, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
     import shutil; lib2 = os.path.join(SCRATCH, f"lib_{abs(hash(str(defs)))}.so"); shutil.copy(lib, lib2)
     L = ctypes.CDLL(lib2)
     for name, (res, args) in _lib.SIGNATURES.items():

@@ -270,6 +270,36 @@ def test_cost_volume_backward_minification_fallback():
     assert torch.equal(gsrc, gsrc2)
 
 
+def test_grad_src_cell_table_and_tile_scan_paths_agree(monkeypatch):
+    """grad_src has two atomic-free implementations: the global cell table (default) and the tile-scan kernels it
+    falls back to when a cell overflows (TMVS_BWD_SRC_PATH=scan forces them).  Same contributions, different fixed
+    summation orders: they agree to fp32 re-association, and each is bit-reproducible.  Cases: cascade shapes with
+    per-pixel hypotheses (parity collisions + overflow slots in use), [B,D] hypotheses, a ragged 37x53 map."""
+    cases = []
+    for stage, hw in ((1, (128, 160)), (2, (144, 200)), (3, (96, 136))):
+        st = synthetic.make_stage(stage, batch=2, n_views=4, height=hw[0], width=hw[1], seed=21)
+        cases.append((st, st.depth_values))
+    st = synthetic.make_stage(2, batch=1, n_views=3, height=74, width=106, seed=22)
+    cases.append((st, st.depth_values))
+    st = synthetic.make_stage(1, batch=2, n_views=3, height=96, width=128, seed=23)
+    cases.append((st, st.depth_values[:, :, 0, 0].contiguous()))            # [B,D] hypotheses
+    for st, dv in cases:
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        packed = ops.pack_sources([cu(f) for f in st.features[1:]])
+        b, d, h, w = st.depth_values.shape
+        gv = cu(torch.randn(len(st.features) - 1, b, d, h, w, generator=torch.Generator().manual_seed(5)))
+        run = lambda: ops.costvol_backward_packed(cu(st.features[0]), packed, rt, cu(dv), gv, need_ref=False)[1]
+        monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+        g_cells, g_cells2 = run(), run()
+        monkeypatch.setenv("TMVS_BWD_SRC_PATH", "scan")
+        g_scan = run()
+        monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+        assert torch.equal(g_cells, g_cells2)
+        assert float((g_cells - g_scan).abs().max()) <= 3e-6 * float(g_scan.abs().max())
+        o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, dv, gv.cpu())
+        assert_costvol_close(g_cells.cpu().numpy(), o_src, f"stage {st.stage} grad_src (cell table)")
+
+
 def test_backward_adjoint_identity_full_size():
     """Size-independent property at the BlendedMVS training size (config 4, one stage-2 item):
     <G, J(src)> == <J^T(G), src> for the linear map src -> per-view similarity."""

@@ -20,10 +20,19 @@
 //   Every output element is written exactly once by its owner, in a fixed summation order: no atomics on
 //   data, bit-reproducible run to run.
 // grad_ref is a plain gather (forward-shaped kernel), split over views and reduced in view order.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tmvs_common.cuh"
 
 extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
                                  float *packed, int B, int C, int H, int W, tmvs_stream_t stream);
+
+// cell-table path of grad_src (tmvs_costvol_bwd_cells.cu)
+size_t tmvs_bwd_cells_bytes_per_pair(int D, int H, int W);
+int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, const float *G, float *grad_src,
+                       char *tables, int pairs_per_pass, int *flags, int *overflow, int b_total, int b_first, int bc,
+                       int n_src, int C, int D, int H, int W, const TmvsGeom &geom, cudaStream_t st);
 
 namespace {
 
@@ -102,9 +111,10 @@ bwd_ref_reduce_kernel(const float *__restrict__ partial, float *__restrict__ gra
 template <bool PER_PIXEL>
 __global__ void __launch_bounds__(kThreads)
 bwd_bbox_kernel(const float *__restrict__ depth, int4 *__restrict__ bbox, int b_first, int b_chunk, int D, int H,
-                int W, int n_tx, int n_tiles, const __grid_constant__ TmvsGeom geom)
+                int W, int n_tx, int n_tiles, const int *__restrict__ gate, const __grid_constant__ TmvsGeom geom)
 {
     __shared__ int red[4][kTY];
+    if (gate && gate[blockIdx.z] == 0) return;   // the cell-table path (tmvs_costvol_bwd_cells.cu) served this pair
     const int x = blockIdx.x * kTX + threadIdx.x;
     const int y = blockIdx.y * kTY + threadIdx.y;
     const bool valid = x < W && y < H;
@@ -184,9 +194,10 @@ constexpr int kSlots2 = 4;           // footprints per cell per plane on the fas
 // Union over ALL planes of the boxes of the 8x8 tiles of a group: the coarse level of the scan.
 __global__ void __launch_bounds__(kThreads)
 bwd_gbox_kernel(const int4 *__restrict__ bbox, int4 *__restrict__ gbox, int D, int n_tx, int n_ty, int n_gx,
-                int n_tiles, int n_groups)
+                int n_tiles, int n_groups, const int *__restrict__ gate)
 {
     __shared__ int red[4][kTY];
+    if (gate && gate[blockIdx.y] == 0) return;
     const int group = blockIdx.x, vb = blockIdx.y;
     const int gy = group / n_gx, gx = group - gy * n_gx;
     const int tid = threadIdx.y * kTX + threadIdx.x;
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, BwdMinBlocks<C4T>::value)
 bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth, const float *__restrict__ G,
                const int4 *__restrict__ bbox, const int4 *__restrict__ gbox, float *__restrict__ grad_src, int b_total,
                int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_tx, int n_ty, int n_tiles,
-               int n_gx, int n_groups, const __grid_constant__ TmvsGeom geom)
+               int n_gx, int n_groups, const int *__restrict__ gate, const __grid_constant__ TmvsGeom geom)
 {
     __shared__ int cell[kPlanes][kSlots2][kCells];
     __shared__ float krec[kPlanes][4][kThreads];
@@ -228,6 +239,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     __shared__ int ghits[kThreads];
     __shared__ int wcount[kTY];
 
+    if (gate && gate[blockIdx.z] == 0) return;   // the cell-table path served this (view, batch) pair
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
     const int s_x = blockIdx.x * kTX, s_y = blockIdx.y * kTY;      // the owned source tile
     const int qx = s_x + tx, qy = s_y + ty;
@@ -425,8 +437,14 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
 inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct BwdWorkspace {
-    size_t ref_packed, partial, bbox, gbox, total;
+    size_t ref_packed, partial, bbox, gbox, flags, tables, total;
+    int pairs_per_pass;      // (view, batch) pairs whose cell tables are resident at once
+    bool cells;              // the cell-table path applies (ids pack y < 2^15, x < 2^16)
 };
+
+#ifndef TMVS_BWD_TABLE_BYTES
+#define TMVS_BWD_TABLE_BYTES (3ull << 30)      // cap of the cell-table workspace; at least one pair always fits
+#endif
 
 inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
 {
@@ -438,7 +456,16 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.bbox = ws.partial + align256((size_t)n_src * B * C * HW * 4);
     ws.gbox = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
     const size_t n_groups = (size_t)(((W + kTX - 1) / kTX + kGroup - 1) / kGroup) * (((H + kTY - 1) / kTY + kGroup - 1) / kGroup);
-    ws.total = ws.gbox + align256((size_t)n_src * B * n_groups * 16);
+    ws.flags = ws.gbox + align256((size_t)n_src * B * n_groups * 16);
+    ws.tables = ws.flags + align256((size_t)3 * n_src * B * sizeof(int));
+    ws.cells = H <= 32767 && W <= 65535;
+    const size_t per_pair = tmvs_bwd_cells_bytes_per_pair(D, H, W);
+    const int b_group = B < TMVS_GEOM_SLOTS / n_src ? B : TMVS_GEOM_SLOTS / n_src;
+    size_t pairs = TMVS_BWD_TABLE_BYTES / per_pair;
+    if (pairs < 1) pairs = 1;
+    if (pairs > (size_t)n_src * b_group) pairs = (size_t)n_src * b_group;
+    ws.pairs_per_pass = (int)pairs;
+    ws.total = ws.tables + (ws.cells ? pairs * per_pair : 0);
     return ws;
 }
 
@@ -446,7 +473,7 @@ template <bool PER_PIXEL>
 int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st, const float4 *packed,
                const float4 *refp, const float *depth, const float *G, float *partial, int4 *bbox, int4 *gbox,
                float *grad_src, int b_total, int b_first, int b_chunk, int C, int D, int H, int W, int n_tx,
-               int n_tiles, const TmvsGeom &geom)
+               int n_tiles, const int *gate, const TmvsGeom &geom)
 {
     dim3 block(kTX, kTY);
     const int n_ty = n_tiles / n_tx;
@@ -458,12 +485,13 @@ int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st,
                                                                        b_chunk, C, c4, D, H, W, geom);             \
         if (want_src) {                                                                                            \
             bwd_bbox_kernel<PER_PIXEL><<<grid, block, 0, st>>>(depth, bbox, b_first, b_chunk, D, H, W, n_tx,       \
-                                                               n_tiles, geom);                                     \
+                                                               n_tiles, gate, geom);                               \
             bwd_gbox_kernel<<<dim3(n_groups, grid.z), block, 0, st>>>(bbox, gbox, D, n_tx, n_ty, n_gx, n_tiles,    \
-                                                                      n_groups);                                   \
+                                                                      n_groups, gate);                             \
             bwd_src_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(refp, depth, G, bbox, gbox, grad_src,       \
                                                                        b_total, b_first, b_chunk, C, c4, D, H, W,  \
-                                                                       n_tx, n_ty, n_tiles, n_gx, n_groups, geom); \
+                                                                       n_tx, n_ty, n_tiles, n_gx, n_groups, gate,  \
+                                                                       geom);                                      \
         }                                                                                                          \
     } while (0)
     if (c4 == 2) TMVS_BWD(2, true);
@@ -503,6 +531,11 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     float *partial = (float *)(wsp + ws.partial);
     int4 *bbox = (int4 *)(wsp + ws.bbox);
     int4 *gbox = (int4 *)(wsp + ws.gbox);
+    int *flags = (int *)(wsp + ws.flags);
+    int *overflow = flags + 2 * (size_t)n_src * B;       // one per (view, batch) pair: set -> the tile-scan kernels redo it
+    // TMVS_BWD_SRC_PATH=scan forces the tile-scan kernels (the robust path the cell tables fall back to)
+    const char *src_path = getenv("TMVS_BWD_SRC_PATH");
+    const bool use_cells = grad_src && ws.cells && !(src_path && strcmp(src_path, "scan") == 0);
     const int c4 = (C + 3) / 4;
     const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY, n_tiles = n_tx * n_ty;
     const size_t HW = (size_t)H * W;
@@ -510,6 +543,10 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         const float *one[1] = {ref};
         int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, stream);
         if (rc != TMVS_OK) return rc;
+        if (use_cells) {
+            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)3 * n_src * B * sizeof(int), st);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     const int b_per_launch = TMVS_GEOM_SLOTS / n_src;
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
@@ -521,16 +558,25 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
                 for (int k = 0; k < 12; ++k)
                     geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
         dim3 grid(n_tx, n_ty, n_src * bc);
-        // the bbox table of this launch is indexed by blockIdx.z = i * bc + bl
         int rc;
+        if (use_cells) {
+            // grad_src through the cell tables; the tile-scan kernels below then run only if a cell overflowed
+            rc = tmvs_bwd_src_cells((const float4 *)refp, depth, per_pixel, grad_views, grad_src, wsp + ws.tables,
+                                    ws.pairs_per_pass, flags + 2 * (size_t)n_src * b0, overflow + (size_t)n_src * b0, B, b0, bc,
+                                    n_src, C, D,
+                                    H, W, geom, st);
+            if (rc != TMVS_OK) return rc;
+        }
+        const int *gate = use_cells ? overflow + (size_t)n_src * b0 : nullptr;
+        // the bbox table of this launch is indexed by blockIdx.z = i * bc + bl
         if (per_pixel)
             rc = launch_bwd<true>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
                                   (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
-                                  W, n_tx, n_tiles, geom);
+                                  W, n_tx, n_tiles, gate, geom);
         else
             rc = launch_bwd<false>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
                                    (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
-                                   W, n_tx, n_tiles, geom);
+                                   W, n_tx, n_tiles, gate, geom);
         if (rc != TMVS_OK) return rc;
     }
     if (grad_ref) {
