@@ -144,6 +144,34 @@ int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float
                                  int B, int D, int H, int W, int n_src, tmvs_stream_t stream);
 
 /*
+ * SURVEY.md 8(f) N4 -- fusibile depth-map fusion (gipuma/fusibile/fusibile.cu:89-173 kernel `fusibile`, :175-210
+ * copy_pc_to_host, :216-285 the per-camera launch / synchronise / host-scan loop; main.cpp:128-147 image set-up).
+ *   images  [V][H][W][4] fp32: b, g, r in [0,1] and w = depth (425 + 512 * alpha/255, main.cpp:137); sampled through
+ *           the texture unit with the reference's settings (float4, bilinear, unnormalised + 0.5).  512-byte aligned,
+ *           W even and H*W a multiple of 32 (pitch-linear texture resources), else TMVS_E_UNSUPPORTED.
+ *   cams    HOST [V][TMVS_FUSE_CAM_FLOATS]: P (3x4 row major), RK_inv = inverse(P[:, :3]) (3x3), camera centre C (3),
+ *           P[:, 3] (3), focal length K[0] of the decomposed P (cameraGeometryUtils.h:104-156).
+ *   depth_threshold 0.25, consistent_threshold 3 (algorithmparameters.h:11-12).
+ *   carry_over != 0 reproduces the reference's output exactly: its per-pixel point buffer is never cleared between
+ *           cameras, so every later camera re-emits a pixel's latest fused point (fusibile.cu:165-166,188);
+ *           0 emits each camera's own points only.
+ *   points  [capacity][8] fp32 out: x, y, z, 0, b, g, r, 0 (point_cloud.h:7-11; the reference's float4 operator+ drops w),
+ *           in the reference's order (camera, then y, then x).  *n_points (device, int64) = number of points found,
+ *           which may exceed capacity (only the first `capacity` are written).
+ * Unlike every other entry point this one synchronises `stream` before returning (it owns texture objects).
+ */
+#define TMVS_FUSE_CAM_FLOATS 28
+#define TMVS_FUSE_MAX_VIEWS 1024       /* config.h:2 MAX_IMAGES */
+int tmvs_fusibile_fwd(const float *images, const float *cams, int V, int H, int W, float depth_threshold,
+                      int consistent_threshold, int carry_over, float *points, long long capacity,
+                      long long *n_points, void *workspace, size_t workspace_bytes, tmvs_stream_t stream);
+size_t tmvs_fusibile_workspace_bytes(int V, int H, int W);
+/* Diagnostic: out[j] = tex2D<float4>(image, uv[j]) through the texture set-up tmvs_fusibile_fwd uses (image [H][W][4],
+ * uv [n][2] unnormalised texture coordinates, out [n][4], all device).  The tests use it to measure the CPU oracle's
+ * emulation of the hardware's 9-bit-weight bilinear filter.  Synchronises `stream`. */
+int tmvs_fusibile_tex_probe(const float *image, int H, int W, const float *uv, float *out, int n, tmvs_stream_t stream);
+
+/*
  * Backward of the cost volume wrt the features (autograd of models/module.py:318-320 and
  * models/TransMVSNet.py:80).  grad_views = dL/d sim_i [Nsrc][B][D][H][W].
  *   grad_ref  [B][C][H][W]            (contiguous NCHW, overwritten)

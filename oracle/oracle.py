@@ -142,3 +142,25 @@ def pixelwise_weights(sim_views, state) -> np.ndarray:
                                            _f(w2), ctypes.c_float(b2), ctypes.c_float(1e-5), _f(wi), b, d, h, w)
         out[:, i] = wi
     return out
+
+
+def fusibile(images, cams, depth_threshold=0.25, consistent_threshold=3, carry_over=True):
+    """images [V,H,W,4] (b, g, r, depth), cams [V,28] -> fused points [n,8]; gipuma/fusibile restated (parity unpinned)."""
+    images, cams = _c(images), _c(cams)
+    v, h, w, _ = images.shape
+    cap = v * h * w
+    pts = np.empty((cap, 8), np.float32)
+    scratch = np.empty((h * w, 8), np.float32)
+    fn = lib().tmvs_oracle_fusibile
+    fn.restype = ctypes.c_longlong
+    n = fn(_f(images), _f(cams), v, h, w, ctypes.c_float(depth_threshold), int(consistent_threshold), int(bool(carry_over)),
+           _f(pts), ctypes.c_longlong(cap), _f(scratch))
+    return pts[:n].copy()
+
+
+def tex_linear(img, uv):
+    """img [H,W,4], uv [n,2] unnormalised texture coordinates -> [n,4]: the oracle's model of the bilinear texture fetch."""
+    img, uv = _c(img), _c(uv)
+    out = np.empty((uv.shape[0], 4), np.float32)
+    lib().tmvs_oracle_tex_linear(_f(img), img.shape[0], img.shape[1], _f(uv), _f(out), uv.shape[0])
+    return out

@@ -29,6 +29,10 @@ SIGNATURES = {
                                        ctypes.c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "tmvs_depth_hypotheses_fwd": (c_int, [_P, c_int, c_int, c_int, ctypes.c_float, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_pixelwise_aggregate_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "tmvs_fusibile_fwd": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.c_float, c_int, c_int, _P, ctypes.c_longlong, _P, _P,
+                                  c_size_t, _P]),
+    "tmvs_fusibile_workspace_bytes": (c_size_t, [c_int] * 3),
+    "tmvs_fusibile_tex_probe": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
     "tmvs_costvol_bwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P,
                                  c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_costvol_bwd_workspace_bytes": (c_size_t, [c_int] * 6),

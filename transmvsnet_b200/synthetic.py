@@ -174,3 +174,42 @@ def make_cascade(*, batch: int = 1, n_views: int = 5, height: int = 1152, width:
     cams = make_cameras(batch, n_views, height, width, kind=kind, seed=seed)
     return [make_stage(s, batch=batch, n_views=n_views, height=height, width=width, kind=kind,
                        seed=seed, cameras=cams) for s in (1, 2, 3)]
+
+
+def make_fusion_scene(n_views: int = 5, height: int = 64, width: int = 96, seed: int = 0, hole_fraction: float = 0.05,
+                      outlier_fraction: float = 0.05):
+    """Inputs of the depth-map fusion: `n_views` DTU-like cameras looking at a tilted plane, each
+    with its exact depth map of the plane (float, not the 8-bit PNG quantisation), random colours, a few holes
+    (depth 0 -> below fusibile's 425.001 floor) and a few outliers (depth off by 3-10 %, rejected by the consistency test).
+
+    Returns (images [V,H,W,4] fp32: b, g, r, depth;  P [V,3,4] fp32 = K [R | t], the matrices test.py writes).
+    """
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    cams = make_cameras(1, n_views, height, width, kind="dtu", seed=seed)
+    pm = cams["stage3"][0].double().numpy()                      # [N,2,4,4]
+    normal = np.array([0.12, -0.08, 1.0])
+    normal /= np.linalg.norm(normal)
+    d0 = 680.0 * normal[2]                                       # plane through (0, 0, 680)
+    ys, xs = np.meshgrid(np.arange(height, dtype=np.float64), np.arange(width, dtype=np.float64), indexing="ij")
+    u = np.stack([xs, ys, np.ones_like(xs)], -1)                 # [H,W,3]
+    images = np.zeros((n_views, height, width, 4), np.float32)
+    Ps = np.zeros((n_views, 3, 4), np.float32)
+    for v in range(n_views):
+        ext, K = pm[v, 0], pm[v, 1, :3, :3]
+        P = (K @ ext[:3, :4]).astype(np.float32)
+        Ps[v] = P
+        Pd = P.astype(np.float64)
+        Minv = np.linalg.inv(Pd[:, :3])
+        # X(lambda) = Minv (lambda u - p4);  n . X = d0  ->  lambda
+        num = d0 + normal @ (Minv @ Pd[:, 3])
+        den = (u @ Minv.T) @ normal
+        depth = num / den
+        depth[(depth < 430.0) | (depth > 930.0)] = 0.0
+        hole = rng.random((height, width)) < hole_fraction
+        outl = rng.random((height, width)) < outlier_fraction
+        depth = np.where(outl, depth * (1.0 + rng.uniform(0.03, 0.10, depth.shape)), depth)
+        depth = np.where(hole, 0.0, depth)
+        images[v, ..., :3] = rng.random((height, width, 3), dtype=np.float32)
+        images[v, ..., 3] = depth.astype(np.float32)
+    return torch.from_numpy(images), torch.from_numpy(Ps)
