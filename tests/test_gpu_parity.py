@@ -505,6 +505,38 @@ def test_pixelwise_aggregate_folded_kernel():
     assert float((got.cpu() - want).abs().max()) <= 1e-5
 
 
+def test_pixelwise_weight_table_matches_the_mlp_in_double():
+    """The kernel evaluates eval-mode PixelwiseNet (a ReLU network of ONE scalar) as a piecewise-linear table built on
+    the host.  Random folded parameters -- including dead first-layer units (w = 0), duplicated hinges and large
+    magnitudes -- and similarities spanning far beyond every breakpoint, against the MLP evaluated in float64."""
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        mlp = rng.normal(0, 1.0 + trial, 177).astype(np.float32)
+        if trial >= 2:
+            mlp[rng.integers(0, 16, 3)] = 0.0                       # dead first-layer units
+            mlp[5], mlp[16 + 5] = mlp[4], mlp[16 + 4]               # two identical hinges
+        if trial == 5:
+            mlp[:16] *= 1e-3                                        # hinges far away from the data
+        n, b, d, h, w = 2, 1, 24, 16, 64
+        sims = (rng.normal(0, 1, (n, b, d, h, w)) * rng.choice([0.01, 1.0, 50.0], (n, b, 1, h, w))).astype(np.float32)
+        vw, agg = tm.pixelwise_aggregate(cu(torch.from_numpy(sims)), torch.from_numpy(mlp))
+        x = sims.astype(np.float64)[..., None]
+        w0, b0 = mlp[:16].astype(np.float64), mlp[16:32].astype(np.float64)
+        w1, b1 = mlp[32:160].astype(np.float64).reshape(8, 16), mlp[160:168].astype(np.float64)
+        w2, b2 = mlp[168:176].astype(np.float64), float(mlp[176])
+        h0 = np.maximum(x * w0 + b0, 0.0)
+        h1 = np.maximum(h0 @ w1.T + b1, 0.0)
+        logit = h1 @ w2 + b2                                        # [n,b,d,h,w]
+        want = 1.0 / (1.0 + np.exp(-logit.max(axis=2)))             # [n,b,h,w]
+        got = vw.cpu().numpy().transpose(1, 0, 2, 3)                # [b,n,h,w] -> [n,b,h,w]
+        scale = max(1.0, float(np.abs(logit).max()))
+        # sigmoid is 1/4-Lipschitz: a logit error of eps moves the weight by <= eps/4; fp32 logits carry ~1e-7 * scale
+        assert np.abs(got - want).max() <= 2e-6 * scale, (trial, float(np.abs(got - want).max()))
+        wsum = 1e-5 + got.sum(0)
+        ref_agg = (sims.astype(np.float64) * got[:, :, None]).sum(0) / wsum[:, None]
+        assert np.abs(agg.cpu().numpy() - ref_agg).max() <= 1e-5 * max(1.0, float(np.abs(ref_agg).max()))
+
+
 def test_depthnet_forward_learned_weights():
     g = golden("depthnet_s1_learned")
     net = tm.DepthNet().eval()

@@ -264,37 +264,118 @@ aggregate_fwd_kernel(const float *__restrict__ sim_views, const float *__restric
     agg[((size_t)b * D + d) * HW + p] = __fdiv_rn(s, wsum);
 }
 
-struct PwnParams {
-    float w0[16], b0[16], w1[8][16], b1[8], w2[8], b2;
+// PixelwiseNet in eval mode is a ReLU network 1 -> 16 -> 8 -> 1 applied to ONE scalar (the similarity of a voxel):
+// as a function of that scalar it is continuous and piecewise linear, with at most 16 (first-layer hinges) + 17 * 8
+// (second-layer sign changes inside each first-layer interval) = 152 breakpoints.  The host tabulates it once per call
+// in double precision (breakpoints + slope/intercept of every segment + a uniform grid that maps a value to a
+// segment to start the search from); the kernel then spends one table look-up and one FMA per voxel instead of the
+// ~170 FMA of the unrolled MLP, and the max over D of sigmoid(.) is one sigmoid of the max logit (monotone).
+constexpr int kPwlSeg = 160;      // >= 153 segments
+constexpr int kPwlCell = 256;
+
+struct PwlTable {
+    float bp[kPwlSeg];            // bp[k] = upper end of segment k (k < nbp); segment nbp is unbounded above
+    float2 ab[kPwlSeg];           // logit = ab.x * x + ab.y on segment k
+    unsigned char cell[kPwlCell]; // segment to start the search from for a value in grid cell c
+    float lo, inv_dx;
+    int nbp;
 };
 
-// PixelwiseNet (eval, BatchNorm folded): one thread per (view, pixel) sweeps the D similarities through the
-// 1 -> 16 -> 8 -> 1 MLP and keeps the maximum logit (sigmoid is monotone: one sigmoid per thread).  The weighted
-// aggregation is then the ordinary aggregate_fwd_kernel, which re-reads the similarities from L2.
-__global__ void __launch_bounds__(256, 4)
-pixelwise_weight_kernel(const float *__restrict__ sim_views, float *__restrict__ vw, int B, int D, size_t HW, int n_src,
-                        const __grid_constant__ PwnParams prm)
+static PwlTable build_pwl(const float *mlp)
 {
+    const float *w0 = mlp, *b0 = mlp + 16, *w1 = mlp + 32, *b1 = mlp + 160, *w2 = mlp + 168;
+    const double b2 = mlp[176];
+    double t[kPwlSeg];
+    int n = 0;
+    auto insert = [&](double v) {
+        if (!(v == v) || v > 1e30 || v < -1e30 || n >= kPwlSeg - 2) return;
+        int k = n;
+        while (k > 0 && t[k - 1] > v) { t[k] = t[k - 1]; --k; }
+        if (k > 0 && t[k - 1] == v) { for (int j = k; j < n; ++j) t[j] = t[j + 1]; return; }
+        t[k] = v;
+        ++n;
+    };
+    for (int c = 0; c < 16; ++c)
+        if (w0[c] != 0.0f) insert(-(double)b0[c] / (double)w0[c]);
+    // affine form of the 8 second-layer pre-activations on the first-layer interval that contains xm
+    auto second_layer = [&](double xm, double *p, double *q) {
+        for (int j = 0; j < 8; ++j) { p[j] = 0.0; q[j] = b1[j]; }
+        for (int c = 0; c < 16; ++c) {
+            if ((double)w0[c] * xm + (double)b0[c] > 0.0)
+                for (int j = 0; j < 8; ++j) { p[j] += (double)w1[j * 16 + c] * w0[c]; q[j] += (double)w1[j * 16 + c] * b0[c]; }
+        }
+    };
+    auto midpoint = [&](const double *tt, int nn, int k) {   // a point strictly inside interval k of nn breakpoints
+        if (nn == 0) return 0.0;
+        if (k == 0) return tt[0] - 1.0;
+        if (k == nn) return tt[nn - 1] + 1.0;
+        return 0.5 * (tt[k - 1] + tt[k]);
+    };
+    double first[17];
+    const int n1 = n;
+    for (int k = 0; k < n1; ++k) first[k] = t[k];
+    for (int k = 0; k <= n1; ++k) {
+        double p[8], q[8];
+        second_layer(midpoint(first, n1, k), p, q);
+        for (int j = 0; j < 8; ++j) {
+            if (p[j] == 0.0) continue;
+            const double r = -q[j] / p[j];
+            const bool above = k == 0 || r > first[k - 1], below = k == n1 || r < first[k];
+            if (above && below) insert(r);
+        }
+    }
+    PwlTable tb;
+    tb.nbp = n;
+    for (int k = 0; k <= n; ++k) {
+        const double xm = midpoint(t, n, k);
+        double p[8], q[8], a = 0.0, b = b2;
+        second_layer(xm, p, q);
+        for (int j = 0; j < 8; ++j)
+            if (p[j] * xm + q[j] > 0.0) { a += (double)w2[j] * p[j]; b += (double)w2[j] * q[j]; }
+        tb.ab[k] = make_float2((float)a, (float)b);
+        tb.bp[k] = k < n ? (float)t[k] : INFINITY;
+    }
+    for (int k = n + 1; k < kPwlSeg; ++k) { tb.ab[k] = tb.ab[n]; tb.bp[k] = INFINITY; }
+    tb.lo = n ? tb.bp[0] : 0.0f;
+    const float hi = n ? tb.bp[n - 1] : 0.0f;
+    tb.inv_dx = hi > tb.lo ? (float)kPwlCell / (hi - tb.lo) : 0.0f;
+    for (int c = 0; c < kPwlCell; ++c) {
+        // start one cell early: the kernel's fp32 cell index may be off by one at a cell edge
+        const float edge = tb.inv_dx > 0.0f ? tb.lo + (float)(c - 1) / tb.inv_dx : tb.lo;
+        int k = 0;
+        while (k < n && tb.bp[k] < edge) ++k;       // breakpoints strictly below the edge are behind us
+        tb.cell[c] = (unsigned char)(k > 0 ? k - 1 : 0);
+    }
+    return tb;
+}
+
+// One thread per (view, pixel) sweeps the D similarities through the tabulated logit and keeps the maximum; the
+// weighted aggregation is then the ordinary aggregate_fwd_kernel, which re-reads the similarities from L2.
+__global__ void __launch_bounds__(256)
+pixelwise_weight_kernel(const float *__restrict__ sim_views, float *__restrict__ vw, int B, int D, size_t HW, int n_src,
+                        const __grid_constant__ PwlTable tb)
+{
+    __shared__ float bp_s[kPwlSeg];
+    __shared__ float2 ab_s[kPwlSeg];
+    __shared__ unsigned char cell_s[kPwlCell];
+    for (int k = threadIdx.x; k < kPwlSeg; k += blockDim.x) { bp_s[k] = tb.bp[k]; ab_s[k] = tb.ab[k]; }
+    for (int k = threadIdx.x; k < kPwlCell; k += blockDim.x) cell_s[k] = tb.cell[k];
+    __syncthreads();
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
     const int i = blockIdx.y, b = blockIdx.z;
     const float *sv = sim_views + (((size_t)i * B + b) * D) * HW + p;
+    const float lo = tb.lo, inv_dx = tb.inv_dx;
+    const int nbp = tb.nbp;
     float best = -INFINITY;
-#pragma unroll 2
+#pragma unroll 4
     for (int d = 0; d < D; ++d) {
         const float x = __ldg(sv + (size_t)d * HW);
-        float h0[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) h0[c] = fmaxf(fmaf(prm.w0[c], x, prm.b0[c]), 0.0f);
-        float o = prm.b2;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float h = prm.b1[j];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) h = fmaf(prm.w1[j][c], h0[c], h);
-            o = fmaf(prm.w2[j], fmaxf(h, 0.0f), o);
-        }
-        best = fmaxf(best, o);
+        const float cf = fminf(fmaxf((x - lo) * inv_dx, 0.0f), (float)(kPwlCell - 1));     // NaN -> cell 0
+        int k = cell_s[(int)cf];
+        while (k < nbp && x >= bp_s[k]) ++k;
+        const float2 ab = ab_s[k];
+        best = fmaxf(best, fmaf(ab.x, x, ab.y));
     }
     vw[((size_t)b * n_src + i) * HW + p] = 1.0f / (1.0f + expf(-best));     // nn.Sigmoid, max over D (TransMVSNet.py:26-28)
 }
@@ -307,8 +388,7 @@ extern "C" int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float 
     if (!sim_views || !mlp || !view_weights || !agg) return TMVS_E_NULL;
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0 || B > 65535) return TMVS_E_SHAPE;
     if (n_src > 65535) return TMVS_E_SHAPE;
-    PwnParams prm;
-    memcpy(&prm, mlp, sizeof(float) * TMVS_PWN_PARAMS);
+    const PwlTable prm = build_pwl(mlp);
     const size_t HW = (size_t)H * W;
     cudaStream_t st = (cudaStream_t)stream;
     pixelwise_weight_kernel<<<dim3((unsigned)((HW + 255) / 256), n_src, B), 256, 0, st>>>(sim_views, view_weights, B, D,
