@@ -58,12 +58,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 # kernels whose full SASS is committed (the hot instantiations); every other kernel gets an opcode histogram
-HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1E", "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1E",
-               "costvol_fwd_kernelILi2ELb1ELb1ELb0ELb1E", "costvol_fwd_kernelILi8ELb1ELb1ELb1ELb0E",
+HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1ELb0E", "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1ELb0E",
+               "costvol_fwd_kernelILi2ELb1ELb1ELb0ELb1ELb0E", "costvol_fwd_kernelILi8ELb1ELb1ELb1ELb0ELb0E",
                "pack_sources_nchw4_kernel", "homo_warp_fwd_kernelILb1E", "softmax_wta_kernelILi48E",
                "softmax_wta_kernelILi32E", "softmax_wta_kernelILi8E", "depth_wta_kernel",
                "bwd_src_kernelILi8ELb1ELb1E", "bwd_ref_kernelILi8ELb1ELb1E", "bwd_bbox_kernelILb1E",
-               "costvol_tma_kernel")
+               "costvol_tma_kernelILi4ELb1ELb0ELb1E", "cells_register_kernelILb1E", "cells_fixup_kernelILi1E",
+               "cells_gather_kernelILi4ELb1E", "fuse_points_kernel", "pixelwise_weight_kernel")
 
 
 def dump_sass(out_dir: str) -> None:
