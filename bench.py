@@ -182,9 +182,22 @@ def run_tmvs_arm(args, workload):
     dev_stages = [pipeline.stage_to_device(s, dev) for s in host]
     vv = voxel_views(host)
     torch.cuda.synchronize()
-    comm = torch.cuda.Stream() if world > 1 else None
+    # Multi-GPU: the stage-3 depth + confidence maps of every view end up on rank 0.  Default transport: the read-out
+    # kernel writes them straight into rank 0's buffer through NVLink peer memory (sharding.PeerMapSink) -- no
+    # collective, no extra kernel.  TMVS_GATHER=nccl keeps the NCCL all_gather on a side stream instead.
+    use_peer = world > 1 and workload["batch"] == 1 and os.environ.get("TMVS_GATHER", "peer") == "peer"
+    comm = torch.cuda.Stream() if (world > 1 and not use_peer) else None
+    sink = None
+    if use_peer:
+        h3, w3 = host[-1].depth_values.shape[2:]
+        sink = sharding.PeerMapSink(2 * world, (h3, w3), dev, dst=0)
+    step_no = [0]
 
     def step():
+        if sink is not None:    # ring of two step-slots per rank: this step's maps land in slot (parity, rank)
+            outs = pipeline.run_cascade(dev_stages, out_maps=sink.slot((step_no[0] & 1) * world + rank))
+            step_no[0] += 1
+            return outs
         outs = pipeline.run_cascade(dev_stages)
         if world > 1:       # gather this view's stage-3 depth + confidence on rank 0, off the compute stream
             maps = torch.stack([outs[-1]["depth"], outs[-1]["photo_confidence"]], 1)    # [B,2,H,W]
@@ -331,7 +344,9 @@ def run_tmvs_arm(args, workload):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload["name"], "voxel_views_per_step": vv,
                        "l2": "inputs larger than L2 (>= 1 GB touched per step)", "view_weights": "given as inputs",
-                       "sharding": "by reference view, one process per GPU" + (", NCCL all_gather of depth+conf" if world > 1 else "")},
+                       "sharding": "by reference view, one process per GPU" + (
+                           ", depth+conf maps written by the read-out kernel into rank 0's buffer over NVLink peer memory"
+                           if use_peer else (", NCCL all_gather of depth+conf" if world > 1 else ""))},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "clocks": sampler.summary(),
         }

@@ -61,6 +61,17 @@ int tmvs_set_reference_arithmetic(int mode);
 int tmvs_get_reference_arithmetic(void);
 
 int tmvs_version(void);
+/*
+ * Peer-mapped gather buffer: the multi-GPU exchange of SURVEY.md 8e (every view's depth + confidence map ends up on
+ * one rank) without a collective.  The gathering rank creates the buffer and ships the 64-byte CUDA IPC handle to the
+ * other ranks of the box (any host channel); each opens it with its own GPU current, which maps the buffer into that
+ * GPU's address space over NVLink / NVSwitch.  The pointer is then an ordinary OUTPUT pointer of the entry points
+ * below -- e.g. depth / conf of tmvs_softmax_wta_fwd -- so the kernel's stores cross the link and nothing else runs.
+ * The only calls of this library that allocate or free device memory (cudaMalloc / cudaFree / IPC open / close).
+ */
+int tmvs_peer_buffer_create(size_t bytes, void **ptr, unsigned char *handle64);   /* zero-filled, current device */
+int tmvs_peer_buffer_open(const unsigned char *handle64, void **ptr);             /* in another process of the box */
+int tmvs_peer_buffer_release(void *ptr, int owner);                               /* owner: cudaFree, else IPC close */
 const char *tmvs_error_string(int code);
 
 /* Bytes of the packed source workspace for the given shape. */

@@ -476,6 +476,26 @@ def test_depth_hypotheses_kernel():
     assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 1e-6 * rng
 
 
+def test_readout_writes_maps_into_caller_buffers_and_peer_sink_slots():
+    """softmax_wta(out_depth=, out_conf=) and run_cascade(out_maps=): the read-out kernel stores its maps where the
+    caller says (on a multi-GPU box: a peer-mapped slot of sharding.PeerMapSink, checked by scripts/check_peer_sink.py;
+    here the single-process form of the sink, whose slots are local memory)."""
+    from transmvsnet_b200 import sharding
+    stages = synthetic.make_cascade(batch=1, n_views=3, height=128, width=192, seed=9)
+    dev_stages = [pipeline.stage_to_device(s, DEV) for s in stages]
+    want = pipeline.run_cascade(dev_stages)[-1]
+    h, w = stages[-1].depth_values.shape[2:]
+    sink = sharding.PeerMapSink(3, (h, w), DEV)
+    got = pipeline.run_cascade(dev_stages, out_maps=sink.slot(1))[-1]
+    assert torch.equal(sink.result()[1, 0], want["depth"][0]) and torch.equal(sink.result()[1, 1], want["photo_confidence"][0])
+    assert got["depth"].data_ptr() == sink.slot(1)[:, 0].data_ptr()             # no staging copy
+    assert float(sink.result()[0].abs().sum()) == 0.0 and float(sink.result()[2].abs().sum()) == 0.0
+    with pytest.raises(RuntimeError):
+        tm.softmax_wta(dev_stages[-1]["logits"], dev_stages[-1]["depth_values"], out_depth=torch.empty(1, h, w + 1, device=DEV))
+    with pytest.raises(RuntimeError):
+        tm.softmax_wta(dev_stages[-1]["logits"], dev_stages[-1]["depth_values"], out_conf=torch.empty(1, h, w))
+
+
 def test_pixelwise_aggregate_folded_kernel():
     """eval-mode PixelwiseNet folded into the aggregation kernel, against the reference's
     view weights / aggregated similarity (golden) and the unfused C oracle."""

@@ -16,6 +16,9 @@ LIB_PATH = os.path.join(_PKG, "lib", "libtmvs_sm100a.so")
 _P = c_void_p
 SIGNATURES = {
     "tmvs_version": (c_int, []),
+    "tmvs_peer_buffer_create": (c_int, [c_size_t, _P, _P]),
+    "tmvs_peer_buffer_open": (c_int, [_P, _P]),
+    "tmvs_peer_buffer_release": (c_int, [_P, c_int]),
     "tmvs_set_reference_arithmetic": (c_int, [c_int]),
     "tmvs_get_reference_arithmetic": (c_int, []),
     "tmvs_error_string": (ctypes.c_char_p, [c_int]),

@@ -5,6 +5,8 @@
 // first maximal, as torch.argmax), the depth gathered at that index and the max-probability
 // confidence.  One thread per pixel; every depth plane is read/written as a coalesced 128-byte
 // row per warp, and the D logits of a pixel stay in registers between the three sweeps.
+#include <string.h>
+
 #include "tmvs_common.cuh"
 
 namespace {
@@ -461,6 +463,43 @@ extern "C" int tmvs_set_reference_arithmetic(int mode)
 extern "C" int tmvs_get_reference_arithmetic(void) { return g_arith_mode; }
 
 extern "C" int tmvs_version(void) { return TMVS_VERSION; }
+
+// ---- peer-mapped gather buffer (sharding.PeerMapSink) -----------------------------------------------------------------
+// The one exchange of the multi-GPU path is "every view's depth + confidence map ends up on one rank".  Instead of a
+// collective, that rank exports ONE buffer through CUDA IPC; every other rank opens it with its own GPU current and
+// cudaIpcMemLazyEnablePeerAccess, which maps the buffer into that GPU's address space over NVLink / NVSwitch.  The
+// returned pointer is an ordinary output pointer for tmvs_softmax_wta_fwd: the kernel's stores cross the link.
+// These three calls are the only ones in the library that allocate or free device memory.
+extern "C" int tmvs_peer_buffer_create(size_t bytes, void **ptr, unsigned char *handle64)
+{
+    if (!ptr || !handle64) return TMVS_E_NULL;
+    if (bytes == 0) return TMVS_E_SHAPE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*ptr, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return (int)e; }
+    memcpy(handle64, &h, 64);
+    return TMVS_OK;
+}
+
+extern "C" int tmvs_peer_buffer_open(const unsigned char *handle64, void **ptr)
+{
+    if (!ptr || !handle64) return TMVS_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? TMVS_OK : (int)e;
+}
+
+extern "C" int tmvs_peer_buffer_release(void *ptr, int owner)
+{
+    if (!ptr) return TMVS_E_NULL;
+    const cudaError_t e = owner ? cudaFree(ptr) : cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? TMVS_OK : (int)e;
+}
 
 extern "C" const char *tmvs_error_string(int code)
 {

@@ -365,10 +365,14 @@ def cost_volume(ref_fea: torch.Tensor, src_feas: Sequence[torch.Tensor], rot_tra
     return agg, views
 
 
-def softmax_wta(logits: torch.Tensor, depth_values: torch.Tensor, want_prob: bool = True):
+def softmax_wta(logits: torch.Tensor, depth_values: torch.Tensor, want_prob: bool = True,
+                out_depth: Optional[torch.Tensor] = None, out_conf: Optional[torch.Tensor] = None):
     """logits, depth_values [B,D,H,W] -> (prob or None, index int64 [B,H,W], depth [B,H,W], conf [B,H,W]).
 
     One pass for models/TransMVSNet.py:99-103 + models/module.py:474-482 (forward only).
+    out_depth / out_conf: contiguous fp32 [B,H,W] tensors the kernel writes the maps into.  They may live on ANOTHER
+    GPU of the box (a peer-mapped slot of sharding.PeerMapSink): the kernel's stores then cross NVLink themselves and
+    the multi-GPU gather of the maps needs no collective.
     """
     lib = _lib.load()
     dev = _need_cuda(logits, depth_values)
@@ -378,8 +382,12 @@ def softmax_wta(logits: torch.Tensor, depth_values: torch.Tensor, want_prob: boo
     logits, depth_values = logits.detach().contiguous(), depth_values.detach().contiguous()
     prob = torch.empty_like(logits) if want_prob else None
     index = torch.empty((b, h, w), dtype=torch.int64, device=dev)
-    depth = torch.empty((b, h, w), dtype=torch.float32, device=dev)
-    conf = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    for name, t in (("out_depth", out_depth), ("out_conf", out_conf)):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != (b, h, w)
+                              or not t.is_contiguous()):
+            raise _lib.TmvsError(f"softmax_wta: {name} must be a contiguous fp32 CUDA tensor [{b},{h},{w}]")
+    depth = out_depth if out_depth is not None else torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    conf = out_conf if out_conf is not None else torch.empty((b, h, w), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.tmvs_softmax_wta_fwd(_ptr(logits), _ptr(depth_values), _ptr(prob), _ptr(index), _ptr(depth),
                                       _ptr(conf), b, d, h, w, _stream())

@@ -30,18 +30,30 @@ def stage_to_device(st: StageInputs, device, non_blocking: bool = True) -> Dict[
             "rot_trans": stage_rot_trans(st.proj_matrix)}
 
 
-def run_stage(dev: Dict[str, object], want_prob: bool = True) -> Dict[str, torch.Tensor]:
-    """One stage with the view weights given: 3 kernel launches, nothing else on the device."""
+def run_stage(dev: Dict[str, object], want_prob: bool = True, out_maps: Optional[torch.Tensor] = None
+              ) -> Dict[str, torch.Tensor]:
+    """One stage with the view weights given: 3 kernel launches, nothing else on the device.
+    out_maps [B,2,H,W] (depth, confidence): where the read-out kernel writes its maps -- e.g. a peer-mapped slot of
+    sharding.PeerMapSink on another GPU."""
     feats = dev["features"]
     packed = ops.pack_sources(feats[1:])
     sim, _ = ops.cost_volume_packed(feats[0], packed, dev["rot_trans"], dev["depth_values"], dev["view_weights"],
                                     False, True)
-    prob, idx, depth, conf = ops.softmax_wta(dev["logits"], dev["depth_values"], want_prob=want_prob)
+    out_d = out_c = None
+    if out_maps is not None:
+        if out_maps.shape[0] != 1:
+            raise ValueError("out_maps is one view's [1,2,H,W] slot")
+        out_d, out_c = out_maps[:, 0], out_maps[:, 1]          # contiguous for B = 1
+    prob, idx, depth, conf = ops.softmax_wta(dev["logits"], dev["depth_values"], want_prob=want_prob,
+                                             out_depth=out_d, out_conf=out_c)
     return {"similarity": sim, "prob_volume": prob, "index": idx, "depth": depth, "photo_confidence": conf}
 
 
-def run_cascade(dev_stages: Sequence[Dict[str, object]], want_prob: bool = True) -> List[Dict[str, torch.Tensor]]:
-    return [run_stage(d, want_prob) for d in dev_stages]
+def run_cascade(dev_stages: Sequence[Dict[str, object]], want_prob: bool = True,
+                out_maps: Optional[torch.Tensor] = None) -> List[Dict[str, torch.Tensor]]:
+    """out_maps: destination of the LAST stage's depth + confidence maps (see run_stage)."""
+    last = len(dev_stages) - 1
+    return [run_stage(d, want_prob, out_maps if n == last else None) for n, d in enumerate(dev_stages)]
 
 
 def pin_stage(st: StageInputs) -> StageInputs:

@@ -53,3 +53,69 @@ def gather_maps(local_maps: torch.Tensor, n_views: int, dst: int = 0, group=None
         for j, v in enumerate(range(r, n_views, world)):
             out[v] = bufs[r][j]
     return out
+
+
+class _RawCuda:
+    """A raw device pointer dressed as a CUDA array (zero-copy `torch.as_tensor`)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerMapSink:
+    """The gather of the per-view maps, fused into the kernel that produces them (single box, NVLink / NVSwitch).
+
+    Rank `dst` owns one buffer [slots, 2, H, W] (depth, confidence) created by tmvs_peer_buffer_create and ships its
+    CUDA IPC handle to the other ranks; each opens it with its own GPU current (tmvs_peer_buffer_open), which maps the
+    buffer into that GPU's address space.  `slot(i)` is then a tensor over GPU `dst`'s memory that this rank's kernels
+    can write: passing it as the read-out kernel's output (ops.softmax_wta(out_depth=, out_conf=),
+    pipeline.run_cascade(out_maps=)) makes the kernel's own stores cross NVLink -- no collective, no staging copy, no
+    extra kernel competing with the cost-volume kernels for SMs.  The only synchronisation is the caller's barrier
+    before rank `dst` reads `result()`.  gather_maps (NCCL / gloo all_gather) remains the transport across boxes.
+    """
+
+    def __init__(self, slots: int, hw, device, dst: int = 0, group=None):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        self._lib = lib
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dst = dst
+        self.device = torch.device(device)
+        shape = (int(slots), 2, int(hw[0]), int(hw[1]))
+        nbytes = 4 * shape[0] * shape[1] * shape[2] * shape[3]
+        self._ptr = ctypes.c_void_p(0)
+        self._owner = self.rank == dst
+        payload = [None]
+        with torch.cuda.device(self.device):
+            if self._owner:
+                handle = (ctypes.c_ubyte * 64)()
+                _lib.check(lib.tmvs_peer_buffer_create(nbytes, ctypes.byref(self._ptr), handle), "tmvs_peer_buffer_create")
+                payload = [bytes(handle)]
+            if self.world > 1:
+                dist.broadcast_object_list(payload, src=dst, group=group)
+            if not self._owner:
+                handle = (ctypes.c_ubyte * 64).from_buffer_copy(payload[0])
+                _lib.check(lib.tmvs_peer_buffer_open(handle, ctypes.byref(self._ptr)), "tmvs_peer_buffer_open")
+            # zero-copy view; torch reads the tensor's device off the pointer (GPU `dst`, also for the peer mapping)
+            self.buffer = torch.as_tensor(_RawCuda(self._ptr.value, shape))
+            if self.buffer.data_ptr() != self._ptr.value:
+                raise RuntimeError("PeerMapSink: torch copied the peer buffer instead of aliasing it")
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def slot(self, index: int) -> torch.Tensor:
+        """[1, 2, H, W] view of slot `index` (peer memory on every rank but `dst`)."""
+        return self.buffer[index:index + 1]
+
+    def result(self) -> Optional[torch.Tensor]:
+        """The whole buffer on rank `dst`, None elsewhere (read it after a barrier that follows every writer's
+        stream synchronisation)."""
+        return self.buffer if self._owner else None
+
+    def close(self) -> None:
+        if self._ptr.value:
+            self.buffer = None
+            self._lib.tmvs_peer_buffer_release(self._ptr, int(self._owner))
+            self._ptr.value = 0
