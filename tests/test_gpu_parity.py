@@ -476,6 +476,37 @@ def test_depth_hypotheses_kernel():
     assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 1e-6 * rng
 
 
+@pytest.mark.parametrize("d,hw", [(8, (64, 96)), (32, (40, 64)), (48, (24, 32)), (24, (16, 32))])
+def test_readout_nan_inf_and_ties_follow_torch(d, hw):
+    """The read-out on rows that break the happy path -- a NaN logit, +inf, -inf, all-equal logits (ties), a huge
+    spread -- against the reference's own statements run by torch on the same GPU (models/TransMVSNet.py:99-103,
+    models/module.py:474-482): probabilities NaN where torch's are, first maximal index, gathered depth, confidence.
+    D = 8 / 32 / 48 take the lean kernels, D = 24 the general one."""
+    torch.manual_seed(d)
+    h, w = hw
+    logits = 3 * torch.randn(2, d, h, w, device=DEV)
+    logits[0, 3, 0, :8] = float("nan")
+    logits[0, d - 1, 1, :8] = float("inf")
+    logits[0, 0, 2, :8] = float("-inf")
+    logits[1, :, 3, :8] = 1.25                                   # exact ties: the first plane wins
+    logits[1, :, 4, :8] *= 40.0                                  # exp underflow for most planes
+    logits[1, 1, 5, :8] = logits[1, 6, 5, :8]                    # a two-way tie somewhere in the middle
+    dv = 425 + 500 * torch.rand(2, d, h, w, device=DEV)
+    prob, idx, dep, conf = tm.softmax_wta(logits, dv)
+    want_p = torch.exp(torch.log_softmax(logits, 1))
+    nan_rows = torch.isnan(want_p).any(1)
+    assert torch.equal(torch.isnan(prob), torch.isnan(want_p))
+    assert float((prob - want_p)[~torch.isnan(want_p)].abs().max()) <= PROB_ABS
+    assert torch.equal(idx, torch.argmax(prob, 1))               # integer output: bit-exact on the kernel's own prob
+    assert torch.equal(idx[nan_rows], torch.zeros_like(idx[nan_rows]))      # torch: first element of an all-NaN row
+    assert torch.equal(dep, torch.gather(dv, 1, idx[:, None])[:, 0])
+    assert torch.equal(torch.isnan(conf), nan_rows) and torch.equal(conf[~nan_rows], prob.max(1)[0][~nan_rows])
+    assert torch.equal(idx[1, 3, :8], torch.zeros_like(idx[1, 3, :8]))
+    none, idx2, dep2, conf2 = tm.softmax_wta(logits, dv, want_prob=False)
+    assert none is None and torch.equal(idx2, idx) and torch.equal(dep2, dep)
+    assert torch.equal(torch.isnan(conf2), torch.isnan(conf)) and torch.equal(conf2[~nan_rows], conf[~nan_rows])
+
+
 def test_readout_writes_maps_into_caller_buffers_and_peer_sink_slots():
     """softmax_wta(out_depth=, out_conf=) and run_cascade(out_maps=): the read-out kernel stores its maps where the
     caller says (on a multi-GPU box: a peer-mapped slot of sharding.PeerMapSink, checked by scripts/check_peer_sink.py;

@@ -141,6 +141,108 @@ softmax_wta_split_kernel(const float *__restrict__ logits, const float *__restri
     }
 }
 
+// ---- lean forms for the cascade's own plane counts (D == PER * SUB exactly, B * D * HW < 2^32) --------------------
+// Same arithmetic as the kernels above -- exp(x - max - log(sum exp(x - max))), first maximal index -- with the
+// bookkeeping stripped: no d < D guards, 32-bit offsets, and plain comparisons instead of the NaN-aware ones.  That is
+// safe HERE because one NaN (or inf - inf) among a pixel's logits makes log(sum) NaN and with it EVERY probability of
+// the pixel; torch.argmax of an all-NaN row is its first element, which is what "keep the first candidate unless a
+// later one compares greater" returns.  (depth_wta below, whose input is an arbitrary volume, keeps the NaN ordering.)
+// The read-out is issue-bound (ncu: 81-88 % issue slots, 20-46 % DRAM), so fewer instructions is the lever.
+template <int PER, int SUB, bool PROB>
+__global__ void __launch_bounds__(32 * SUB)
+softmax_wta_split_lean_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
+                              int64_t *__restrict__ index, float *__restrict__ depth, float *__restrict__ conf,
+                              unsigned HW)
+{
+    constexpr int D = PER * SUB;
+    __shared__ float sh_a[SUB][32];
+    __shared__ float sh_b[SUB][32];
+    __shared__ int sh_i[SUB][32];
+    const int lane = threadIdx.x, sub = threadIdx.y;
+    const unsigned p = blockIdx.x * 32u + lane;
+    const bool live = p < HW;
+    const unsigned base = blockIdx.y * (unsigned)D * HW + (live ? p : 0u) + (unsigned)sub * HW;   // plane sub, then += SUB planes
+    const unsigned step = (unsigned)SUB * HW;
+    float v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) v[k] = __ldcs(logits + base + k * step);
+    float m = v[0];
+#pragma unroll
+    for (int k = 1; k < PER; ++k) m = fmaxf(m, v[k]);
+    sh_a[sub][lane] = m;
+    __syncthreads();
+    m = sh_a[0][lane];
+#pragma unroll
+    for (int j = 1; j < SUB; ++j) m = fmaxf(m, sh_a[j][lane]);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] -= m; s += expf(v[k]); }
+    sh_b[sub][lane] = s;
+    __syncthreads();
+    s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SUB; ++j) s += sh_b[j][lane];
+    const float ls = logf(s);
+    float best = expf(v[0] - ls);
+    int bk = 0;
+    if (PROB && live) prob[base] = best;
+#pragma unroll
+    for (int k = 1; k < PER; ++k) {
+        const float pv = expf(v[k] - ls);
+        if (PROB && live) prob[base + k * step] = pv;
+        if (pv > best) { best = pv; bk = k; }
+    }
+    sh_a[sub][lane] = best;            // every thread passed the first barrier: its max slot is free again
+    sh_i[sub][lane] = sub + SUB * bk;
+    __syncthreads();
+    if (sub == 0 && live) {
+        int bi = sh_i[0][lane];
+#pragma unroll
+        for (int j = 1; j < SUB; ++j) {
+            const float pj = sh_a[j][lane];
+            const int ij = sh_i[j][lane];
+            if (pj > best || (pj == best && ij < bi)) { best = pj; bi = ij; }
+        }
+        const unsigned o = blockIdx.y * HW + p;
+        index[o] = bi;
+        depth[o] = __ldg(dv + blockIdx.y * (unsigned)D * HW + (unsigned)bi * HW + p);
+        conf[o] = best;
+    }
+}
+
+template <int DT, bool PROB>
+__global__ void __launch_bounds__(256)
+softmax_wta_lean_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
+                        int64_t *__restrict__ index, float *__restrict__ depth, float *__restrict__ conf, unsigned HW)
+{
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const unsigned base = blockIdx.y * (unsigned)DT * HW + p;
+    float v[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = __ldcs(logits + base + d * HW);
+    float m = v[0];
+#pragma unroll
+    for (int d = 1; d < DT; ++d) m = fmaxf(m, v[d]);
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) { v[d] -= m; s += expf(v[d]); }
+    const float ls = logf(s);
+    float best = expf(v[0] - ls);
+    int bi = 0;
+    if (PROB) prob[base] = best;
+#pragma unroll
+    for (int d = 1; d < DT; ++d) {
+        const float pv = expf(v[d] - ls);
+        if (PROB) prob[base + d * HW] = pv;
+        if (pv > best) { best = pv; bi = d; }
+    }
+    const unsigned o = blockIdx.y * HW + p;
+    index[o] = bi;
+    depth[o] = __ldg(dv + base + (unsigned)bi * HW);
+    conf[o] = best;
+}
+
 // Any D (<= TMVS_MAX_DEPTH): re-reads the logits for each sweep (they sit in L1/L2).
 __global__ void __launch_bounds__(256)
 softmax_wta_generic_kernel(const float *__restrict__ logits, const float *__restrict__ dv, float *__restrict__ prob,
@@ -369,6 +471,18 @@ extern "C" int tmvs_softmax_wta_fwd(const float *logits, const float *depth_valu
         logits, depth_values, prob, index, depth, conf, D, HW)
     // one thread per pixel saturates the machine from ~1 M pixels; below that the planes are split over threads
     const bool small = (size_t)B * HW < ((size_t)1 << 20);
+    // the cascade's own plane counts (48 / 32 / 8) with 32-bit offsets: the lean kernels
+    if ((size_t)B * D * HW < 0xffffffffull && (D == 8 || (small && (D == 32 || D == 48)))) {
+        const unsigned hw = (unsigned)HW;
+        const dim3 sgrid((unsigned)((HW + 31) / 32), B), sblock(32, 8);
+#define TMVS_RO_LEAN(PROB)                                                                                              \
+        if (D == 8) softmax_wta_lean_kernel<8, PROB><<<grid, 256, 0, st>>>(logits, depth_values, prob, index, depth, conf, hw); \
+        else if (D == 32) softmax_wta_split_lean_kernel<4, 8, PROB><<<sgrid, sblock, 0, st>>>(logits, depth_values, prob, index, depth, conf, hw); \
+        else softmax_wta_split_lean_kernel<6, 8, PROB><<<sgrid, sblock, 0, st>>>(logits, depth_values, prob, index, depth, conf, hw)
+        if (prob) { TMVS_RO_LEAN(true); } else { TMVS_RO_LEAN(false); }
+#undef TMVS_RO_LEAN
+        return tmvs_launch_status();
+    }
     if (D <= 8) TMVS_RO(8);
     else if (small && D <= 32 && D > 16) TMVS_RO_SPLIT(4, 8);
     else if (small && D <= 48 && D > 32) TMVS_RO_SPLIT(6, 8);
