@@ -32,6 +32,15 @@ def test_homo_warping_golden(name):
     assert np.array_equal(out.cpu().numpy() == 0, g["out"] == 0)       # zero padding / z<1e-6 exactly
 
 
+def test_homo_warping_refuses_to_drop_gradients():
+    g = golden(WARP_CASES[0])
+    src = cu(g["src"]).requires_grad_(True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        tm.homo_warping(src, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"]))
+    with torch.no_grad():
+        assert tm.homo_warping(src, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"])).requires_grad is False
+
+
 def test_homo_warping_channels_last_and_oracle():
     st = synthetic.make_stage(2, batch=2, n_views=3, height=64, width=96, seed=9)
     src = st.features[1]

@@ -110,8 +110,14 @@ def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.
     """Drop-in for models/module.py:284-322 (forward only; the fused path carries the autograd).
 
     src_fea [B,C,H,W]; src_proj, ref_proj [B,4,4]; depth_values [B,D] or [B,D,H,W] -> [B,C,D,H,W].
+    Raises when a gradient would have to flow through the warped volume (training with only this function patched):
+    the volume's general gradient does not have the rank-1 form the fused backward exploits, and returning a detached
+    tensor would silently zero the feature gradients.  Training goes through cost_volume / DepthNet (patch_reference).
     """
     _need_cuda(src_fea, depth_values)
+    if torch.is_grad_enabled() and (src_fea.requires_grad or depth_values.requires_grad):
+        raise _lib.TmvsError("homo_warping is forward-only: for training use transmvsnet_b200.cost_volume / DepthNet "
+                             "(patch_reference), whose autograd runs the atomic-free backward kernels")
     with torch.no_grad():
         rt = relative_rot_trans(src_proj.float(), ref_proj.float())
         packed = pack_sources([src_fea.detach()])
