@@ -309,6 +309,25 @@ def test_grad_src_cell_table_and_tile_scan_paths_agree(monkeypatch):
         assert_costvol_close(g_cells.cpu().numpy(), o_src, f"stage {st.stage} grad_src (cell table)")
 
 
+def test_grad_src_cell_table_multi_group_and_multi_pass(monkeypatch):
+    """Plumbing of the cell-table path: a batch that needs two launch groups (rot/trans travel as kernel parameters,
+    64 (view, batch) slots per launch) and a table workspace capped so that the pairs of a group go through the tables
+    in several passes (TMVS_BWD_TABLE_MB) -- same result as the uncapped run, bit for bit, and equal to the oracle."""
+    st = synthetic.make_stage(2, batch=23, n_views=4, height=32, width=48, seed=17)       # 3 x 23 = 69 pairs > 64
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    n, (b, d, h, w) = 3, st.depth_values.shape
+    gv = torch.randn(n, b, d, h, w, generator=torch.Generator().manual_seed(6))
+    o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, gv)
+    monkeypatch.delenv("TMVS_BWD_TABLE_MB", raising=False)
+    gref, gsrc = _backward_once(st, rt, cu(gv))
+    assert_costvol_close(gref.cpu().numpy(), o_ref, "two launch groups grad_ref")
+    assert_costvol_close(gsrc.cpu().numpy(), o_src, "two launch groups grad_src")
+    monkeypatch.setenv("TMVS_BWD_TABLE_MB", "1")                 # ~1.3 MB per pair at this size: one pair per pass
+    _, gsrc_capped = _backward_once(st, rt, cu(gv))
+    monkeypatch.delenv("TMVS_BWD_TABLE_MB", raising=False)
+    assert torch.equal(gsrc, gsrc_capped)
+
+
 def test_backward_adjoint_identity_full_size():
     """Size-independent property at the BlendedMVS training size (config 4, one stage-2 item):
     <G, J(src)> == <J^T(G), src> for the linear map src -> per-view similarity."""

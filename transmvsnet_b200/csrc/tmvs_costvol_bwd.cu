@@ -461,7 +461,10 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.cells = H <= 32767 && W <= 65535;
     const size_t per_pair = tmvs_bwd_cells_bytes_per_pair(D, H, W);
     const int b_group = B < TMVS_GEOM_SLOTS / n_src ? B : TMVS_GEOM_SLOTS / n_src;
-    size_t pairs = TMVS_BWD_TABLE_BYTES / per_pair;
+    // TMVS_BWD_TABLE_MB (environment) overrides the cap, e.g. to exercise the multi-pass path on small inputs
+    const char *cap_env = getenv("TMVS_BWD_TABLE_MB");
+    const size_t cap = cap_env ? (size_t)atoll(cap_env) << 20 : (size_t)TMVS_BWD_TABLE_BYTES;
+    size_t pairs = cap / per_pair;
     if (pairs < 1) pairs = 1;
     if (pairs > (size_t)n_src * b_group) pairs = (size_t)n_src * b_group;
     ws.pairs_per_pass = (int)pairs;
