@@ -328,6 +328,37 @@ def test_grad_src_cell_table_multi_group_and_multi_pass(monkeypatch):
     assert torch.equal(gsrc, gsrc_capped)
 
 
+def test_grad_src_local_overflow_falls_back_per_tile(monkeypatch):
+    """A steep ramp in the hypotheses of one image region makes dozens of reference pixels land on the same source
+    pixel there (more than a cell's 4 + 2 slots): the footprints that find no slot flag only the 32x8 source tiles they
+    touch, the tile-scan kernels redo exactly those tiles and the cell tables serve the rest.  Result: equal to the
+    oracle, to the forced tile scan (fp32 re-association) and bit-reproducible."""
+    st = synthetic.make_stage(2, batch=1, n_views=4, height=192, width=256, seed=19)
+    dv = st.depth_values.clone()
+    d, h, w = dv.shape[1:]
+    xs = torch.arange(40, dtype=torch.float32)
+    # disparity of a 100 mm baseline at this scale is ~ f*b/z with f*b ~ 2.3e4 px*mm: z(x) = f*b / (c - x) keeps
+    # x + disparity(x) constant, i.e. the whole 40-pixel run maps to (nearly) one source column
+    ramp = 2.3e4 / (64.0 - xs)                                   # 360 .. 960 mm, clipped below
+    dv[:, :, 30:70, 40:80] = ramp.clamp(430.0, 930.0)[None, None, None, :] + torch.linspace(-3, 3, d)[None, :, None, None]
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    gv = torch.randn(3, 1, d, h, w, generator=torch.Generator().manual_seed(8))
+    o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, dv, gv)
+    packed = ops.pack_sources([cu(f) for f in st.features[1:]])
+    run = lambda: ops.costvol_backward_packed(cu(st.features[0]), packed, rt, cu(dv), cu(gv), need_ref=False)[1]
+    monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+    a, b2 = run(), run()
+    monkeypatch.setenv("TMVS_BWD_SRC_PATH", "scan")
+    scan = run()
+    monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+    assert torch.equal(a, b2)
+    assert_costvol_close(a.cpu().numpy(), o_src, "locally minified grad_src")
+    assert float((a - scan).abs().max()) <= 3e-6 * float(scan.abs().max())
+    # the two paths really were mixed: some tiles bit-equal to the scan result (redone by it), others not
+    tiles_equal = (a == scan).flatten(0, 2).reshape(-1, h // 8, 8, w // 32, 32).all(0).all(1).all(2)
+    assert bool(tiles_equal.any()) and not bool(tiles_equal.all())
+
+
 def test_backward_adjoint_identity_full_size():
     """Size-independent property at the BlendedMVS training size (config 4, one stage-2 item):
     <G, J(src)> == <J^T(G), src> for the linear map src -> per-view similarity."""

@@ -31,7 +31,8 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
 // cell-table path of grad_src (tmvs_costvol_bwd_cells.cu)
 size_t tmvs_bwd_cells_bytes_per_pair(int D, int H, int W);
 int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, const float *G, float *grad_src,
-                       char *tables, int pairs_per_pass, int *flags, int *overflow, int b_total, int b_first, int bc,
+                       char *tables, int pairs_per_pass, int *flags, int *overflow, int *tile_overflow, int b_total,
+                       int b_first, int bc,
                        int n_src, int C, int D, int H, int W, const TmvsGeom &geom, cudaStream_t st);
 
 namespace {
@@ -239,7 +240,8 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     __shared__ int ghits[kThreads];
     __shared__ int wcount[kTY];
 
-    if (gate && gate[blockIdx.z] == 0) return;   // the cell-table path served this (view, batch) pair
+    // the cell-table path served every tile but those a slot-less footprint touches
+    if (gate && gate[(size_t)blockIdx.z * n_tiles + blockIdx.y * n_tx + blockIdx.x] == 0) return;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
     const int s_x = blockIdx.x * kTX, s_y = blockIdx.y * kTY;      // the owned source tile
     const int qx = s_x + tx, qy = s_y + ty;
@@ -457,7 +459,7 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.gbox = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
     const size_t n_groups = (size_t)(((W + kTX - 1) / kTX + kGroup - 1) / kGroup) * (((H + kTY - 1) / kTY + kGroup - 1) / kGroup);
     ws.flags = ws.gbox + align256((size_t)n_src * B * n_groups * 16);
-    ws.tables = ws.flags + align256((size_t)3 * n_src * B * sizeof(int));
+    ws.tables = ws.flags + align256((size_t)(3 + n_tiles) * n_src * B * sizeof(int));
     ws.cells = H <= 32767 && W <= 65535;
     const size_t per_pair = tmvs_bwd_cells_bytes_per_pair(D, H, W);
     const int b_group = B < TMVS_GEOM_SLOTS / n_src ? B : TMVS_GEOM_SLOTS / n_src;
@@ -476,7 +478,7 @@ template <bool PER_PIXEL>
 int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st, const float4 *packed,
                const float4 *refp, const float *depth, const float *G, float *partial, int4 *bbox, int4 *gbox,
                float *grad_src, int b_total, int b_first, int b_chunk, int C, int D, int H, int W, int n_tx,
-               int n_tiles, const int *gate, const TmvsGeom &geom)
+               int n_tiles, const int *gate, const int *gate_tile, const TmvsGeom &geom)
 {
     dim3 block(kTX, kTY);
     const int n_ty = n_tiles / n_tx;
@@ -493,8 +495,8 @@ int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st,
                                                                       n_groups, gate);                             \
             bwd_src_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(refp, depth, G, bbox, gbox, grad_src,       \
                                                                        b_total, b_first, b_chunk, C, c4, D, H, W,  \
-                                                                       n_tx, n_ty, n_tiles, n_gx, n_groups, gate,  \
-                                                                       geom);                                      \
+                                                                       n_tx, n_ty, n_tiles, n_gx, n_groups,        \
+                                                                       gate_tile, geom);                           \
         }                                                                                                          \
     } while (0)
     if (c4 == 2) TMVS_BWD(2, true);
@@ -535,7 +537,8 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     int4 *bbox = (int4 *)(wsp + ws.bbox);
     int4 *gbox = (int4 *)(wsp + ws.gbox);
     int *flags = (int *)(wsp + ws.flags);
-    int *overflow = flags + 2 * (size_t)n_src * B;       // one per (view, batch) pair: set -> the tile-scan kernels redo it
+    int *overflow = flags + 2 * (size_t)n_src * B;       // one per (view, batch) pair: some tile of it needs the tile scan
+    int *tile_overflow = overflow + (size_t)n_src * B;   // one per (pair, 32x8 source tile): that tile needs the tile scan
     // TMVS_BWD_SRC_PATH=scan forces the tile-scan kernels (the robust path the cell tables fall back to)
     const char *src_path = getenv("TMVS_BWD_SRC_PATH");
     const bool use_cells = grad_src && ws.cells && !(src_path && strcmp(src_path, "scan") == 0);
@@ -547,7 +550,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, stream);
         if (rc != TMVS_OK) return rc;
         if (use_cells) {
-            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)3 * n_src * B * sizeof(int), st);
+            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(3 + n_tiles) * n_src * B * sizeof(int), st);
             if (e != cudaSuccess) return (int)e;
         }
     }
@@ -565,21 +568,22 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         if (use_cells) {
             // grad_src through the cell tables; the tile-scan kernels below then run only if a cell overflowed
             rc = tmvs_bwd_src_cells((const float4 *)refp, depth, per_pixel, grad_views, grad_src, wsp + ws.tables,
-                                    ws.pairs_per_pass, flags + 2 * (size_t)n_src * b0, overflow + (size_t)n_src * b0, B, b0, bc,
-                                    n_src, C, D,
+                                    ws.pairs_per_pass, flags + 2 * (size_t)n_src * b0, overflow + (size_t)n_src * b0,
+                                    tile_overflow + (size_t)n_src * b0 * n_tiles, B, b0, bc, n_src, C, D,
                                     H, W, geom, st);
             if (rc != TMVS_OK) return rc;
         }
         const int *gate = use_cells ? overflow + (size_t)n_src * b0 : nullptr;
+        const int *gate_tile = use_cells ? tile_overflow + (size_t)n_src * b0 * n_tiles : nullptr;
         // the bbox table of this launch is indexed by blockIdx.z = i * bc + bl
         if (per_pixel)
             rc = launch_bwd<true>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
                                   (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
-                                  W, n_tx, n_tiles, gate, geom);
+                                  W, n_tx, n_tiles, gate, gate_tile, geom);
         else
             rc = launch_bwd<false>(c4, grad_ref != nullptr, grad_src != nullptr, grid, st, (const float4 *)packed,
                                    (const float4 *)refp, depth, grad_views, partial, bbox, gbox, grad_src, B, b0, bc, C, D, H,
-                                   W, n_tx, n_tiles, gate, geom);
+                                   W, n_tx, n_tiles, gate, gate_tile, geom);
         if (rc != TMVS_OK) return rc;
     }
     if (grad_ref) {

@@ -12,8 +12,8 @@
 //                surface folds over, so in the common case every footprint owns its slot after one plain store.
 //   2. fix-up    (p, d) pairs that lost their slot to another pixel of the same parity (detected by reading the slot
 //                back in the next kernel -- the kernel boundary is the only synchronisation) move to overflow slot
-//                1, the losers of that to overflow slot 2; whoever is still homeless raises the overflow flag of its
-//                (view, batch) pair and that pair is redone by the tile-scan kernels of tmvs_costvol_bwd.cu (bwd_src_kernel), which
+//                1, the losers of that to overflow slot 2; whoever is still homeless flags the 32x8 source tiles its
+//                footprint touches, and exactly those tiles are redone by the tile-scan kernels of tmvs_costvol_bwd.cu (bwd_src_kernel), which
 //                handle any multiplicity.  Each fix-up kernel returns at once when the level before it had no loser.
 //   3. gather    one thread OWNS one source pixel q of one view: for d = 0..D-1, for the four tap classes
 //                (nw, ne, sw, se), it reads the cell whose footprints hit q with that tap, sorts the <= 6 ids, and
@@ -37,8 +37,10 @@ struct CellTables {
     uint2 *ovf;         // [nvb][D][ncell]  overflow slots 1, 2
     float2 *pos;        // [nvb][D][HW]     sample position (ix, iy) of (p, d)
     int *flags;         // [0] losers after the parity level, [1] losers after overflow slot 1
-    int *overflow;      // [pair z of the launch group] raised when a footprint of that (view, batch) pair found no slot:
-                        // the caller's tile-scan fallback redoes that pair
+    int *overflow;      // [pair z of the launch group] raised when a footprint of that (view, batch) pair found no slot
+    int *tile_overflow; // [pair z][32x8 source tile]: the tiles such a footprint touches -- the caller's tile-scan fallback
+                        // redoes exactly those tiles, the gather below skips them
+    int n_tx, n_tiles;
 };
 
 // Registration stores are RELAXED (morally strong) device-scope stores: several footprints may store to the same slot
@@ -113,7 +115,17 @@ cells_fixup_kernel(CellTables tb, int z0, int D, int H, int W, int n_dchunks)
             st_relaxed_u32(reinterpret_cast<unsigned *>(tb.flags + 1), 1u);
             continue;
         }
-        if (tb.ovf[cell].y != id) st_relaxed_u32(reinterpret_cast<unsigned *>(tb.overflow + z0 + zl), 1u);
+        if (tb.ovf[cell].y != id) {
+            // homeless: flag the pair and every source tile the footprint touches
+            st_relaxed_u32(reinterpret_cast<unsigned *>(tb.overflow + z0 + zl), 1u);
+            int *tf = tb.tile_overflow + (size_t)(z0 + zl) * tb.n_tiles;
+            const int xa = max(t.x0, 0) / kTX, xb = min(t.x0 + 1, W - 1) / kTX;
+            const int ya = max(t.y0, 0) / kTY, yb = min(t.y0 + 1, H - 1) / kTY;
+            st_relaxed_u32(reinterpret_cast<unsigned *>(tf + ya * tb.n_tx + xa), 1u);
+            st_relaxed_u32(reinterpret_cast<unsigned *>(tf + ya * tb.n_tx + xb), 1u);
+            st_relaxed_u32(reinterpret_cast<unsigned *>(tf + yb * tb.n_tx + xa), 1u);
+            st_relaxed_u32(reinterpret_cast<unsigned *>(tf + yb * tb.n_tx + xb), 1u);
+        }
     }
 }
 
@@ -147,7 +159,8 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
                     int H, int W)
 {
     const int zl = blockIdx.z, z = z0 + zl;
-    if (tb.overflow[z] != 0) return;                          // the tile-scan fallback redoes this (view, batch) pair
+    // a tile touched by a footprint that found no slot is redone, whole, by the tile-scan fallback
+    if (tb.tile_overflow[(size_t)z * tb.n_tiles + blockIdx.y * tb.n_tx + blockIdx.x] != 0) return;
     const int qx = blockIdx.x * kTX + threadIdx.x, qy = blockIdx.y * kTY + threadIdx.y;
     if (qx >= W || qy >= H) return;
     const int i = z / b_chunk, bl = z - i * b_chunk, b = b_first + bl;
@@ -267,9 +280,11 @@ size_t tmvs_bwd_cells_bytes_per_pair(int D, int H, int W)
 
 // grad_src of the (view, batch) pairs z = 0 .. n_src*bc-1 of one launch group (geom.rt[z], z = view * bc + bl),
 // `pairs_per_pass` pairs at a time through the table workspace `tables` (pairs_per_pass * bytes_per_pair bytes).
-// flags: 2 ints per pass (zeroed by the caller); overflow: one int per pair of the group (zeroed by the caller).
+// flags: 2 ints per pass; overflow: one int per pair of the group; tile_overflow: one int per (pair, 32x8 source tile)
+// -- all zeroed by the caller.
 int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, const float *G, float *grad_src,
-                       char *tables, int pairs_per_pass, int *flags, int *overflow, int b_total, int b_first, int bc,
+                       char *tables, int pairs_per_pass, int *flags, int *overflow, int *tile_overflow, int b_total,
+                       int b_first, int bc,
                        int n_src, int C, int D, int H, int W, const TmvsGeom &geom, cudaStream_t st)
 {
     const int c4 = (C + 3) / 4;
@@ -289,6 +304,9 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         tb.pos = reinterpret_cast<float2 *>(tables + (size_t)pairs_per_pass * cell_bytes);
         tb.flags = flags + 2 * pass;
         tb.overflow = overflow;
+        tb.tile_overflow = tile_overflow;
+        tb.n_tx = n_tx;
+        tb.n_tiles = n_tx * n_ty;
         cudaError_t e = cudaMemsetAsync(tables, 0xff, (size_t)nz * D * ncell * (sizeof(uint4) + sizeof(uint2)), st);
         if (e != cudaSuccess) return (int)e;
         dim3 grid_pd(n_tx, n_ty, nz * n_dchunks);
