@@ -334,14 +334,20 @@ def test_grad_src_local_overflow_falls_back_per_tile(monkeypatch):
     touch, the tile-scan kernels redo exactly those tiles and the cell tables serve the rest.  Result: equal to the
     oracle, to the forced tile scan (fp32 re-association) and bit-reproducible."""
     st = synthetic.make_stage(2, batch=1, n_views=4, height=192, width=256, seed=19)
+    rt = geometry.stage_rot_trans(st.proj_matrix)
     dv = st.depth_values.clone()
     d, h, w = dv.shape[1:]
-    xs = torch.arange(40, dtype=torch.float32)
-    # disparity of a 100 mm baseline at this scale is ~ f*b/z with f*b ~ 2.3e4 px*mm: z(x) = f*b / (c - x) keeps
-    # x + disparity(x) constant, i.e. the whole 40-pixel run maps to (nearly) one source column
-    ramp = 2.3e4 / (64.0 - xs)                                   # 360 .. 960 mm, clipped below
-    dv[:, :, 30:70, 40:80] = ramp.clamp(430.0, 930.0)[None, None, None, :] + torch.linspace(-3, 3, d)[None, :, None, None]
-    rt = geometry.stage_rot_trans(st.proj_matrix)
+    # hypotheses for a 40x40 patch chosen so that, for source view 0, every pixel of a patch row projects onto the SAME
+    # source column: x_src = (R0.u z + t0) / (R2.u z + t2) = X  =>  z = (X t2 - t0) / (R0.u - X R2.u)
+    R = rt[0, 0, :9].double().reshape(3, 3).numpy()
+    t = rt[0, 0, 9:].double().numpy()
+    ys, xs = np.meshgrid(np.arange(30, 70), np.arange(40, 80), indexing="ij")
+    u = np.stack([xs, ys, np.ones_like(xs)], -1).astype(np.float64)             # [40,40,3]
+    centre = np.array([60.0, 50.0, 1.0])
+    X = ((R[0] @ centre) * 680.0 + t[0]) / ((R[2] @ centre) * 680.0 + t[2])
+    z = (X * t[2] - t[0]) / (u @ R[0] - X * (u @ R[2]))
+    z = np.clip(z, 440.0, 920.0)
+    dv[:, :, 30:70, 40:80] = torch.from_numpy(z).float()[None, None] + torch.linspace(-2, 2, d)[None, :, None, None]
     gv = torch.randn(3, 1, d, h, w, generator=torch.Generator().manual_seed(8))
     o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, dv, gv)
     packed = ops.pack_sources([cu(f) for f in st.features[1:]])
@@ -355,7 +361,7 @@ def test_grad_src_local_overflow_falls_back_per_tile(monkeypatch):
     assert_costvol_close(a.cpu().numpy(), o_src, "locally minified grad_src")
     assert float((a - scan).abs().max()) <= 3e-6 * float(scan.abs().max())
     # the two paths really were mixed: some tiles bit-equal to the scan result (redone by it), others not
-    tiles_equal = (a == scan).flatten(0, 2).reshape(-1, h // 8, 8, w // 32, 32).all(0).all(1).all(2)
+    tiles_equal = (a == scan)[0, 0].reshape(-1, h // 8, 8, w // 32, 32).all(0).all(1).all(2)     # view 0, [tiles_y, tiles_x]
     assert bool(tiles_equal.any()) and not bool(tiles_equal.all())
 
 
