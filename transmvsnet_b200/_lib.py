@@ -10,7 +10,8 @@ import os
 from ctypes import c_int, c_int64, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libtmvs_sm100a.so")
+# TMVS_LIB_PATH: load another build of the same library (scripts/check_bounds.py uses it for the bounds-checking build)
+LIB_PATH = os.environ.get("TMVS_LIB_PATH") or os.path.join(_PKG, "lib", "libtmvs_sm100a.so")
 
 # every symbol include/tmvs.h declares: name -> (restype, argtypes)
 _P = c_void_p

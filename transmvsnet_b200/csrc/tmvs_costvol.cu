@@ -150,6 +150,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
             }
             float s = 0.0f;
             if (any) {
+                TMVS_ASSERT(max(max(o00, o01), max(o10, o11)) + (EXACT ? C4T - 1 : c4 - 1) * 8u < (unsigned)(H * kc.row));
                 const float4 *p00 = tmvs_pk_ptr(img, o00);
                 const float4 *p01 = tmvs_pk_ptr(img, o01);
                 const float4 *p10 = tmvs_pk_ptr(img, o10);

@@ -77,6 +77,7 @@ cells_register_kernel(const float *__restrict__ depth, CellTables tb, int z0, in
         const TmvsTaps t = tmvs_footprint(c.x, c.y, dims);
         const size_t plane = (size_t)zl * D + d;
         tb.pos[plane * HW + pix] = c;
+        TMVS_ASSERT(!t.any || cell_of(t, W) < ncell);
         if (t.any) st_relaxed_u32(reinterpret_cast<unsigned *>(tb.par + plane * ncell + cell_of(t, W)) + cls, id);
     }
 }
@@ -102,6 +103,7 @@ cells_fixup_kernel(CellTables tb, int z0, int D, int H, int W, int n_dchunks)
         const float2 c = tb.pos[plane * HW + pix];
         const TmvsTaps t = tmvs_footprint(c.x, c.y, dims);
         if (!t.any) continue;
+        TMVS_ASSERT(cell_of(t, W) < ncell);
         const size_t cell = plane * ncell + cell_of(t, W);
         if (reinterpret_cast<const unsigned *>(tb.par + cell)[cls] == id) continue;
         if (LEVEL == 1) {
@@ -191,6 +193,7 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
 #pragma unroll
         for (int cls = 0; cls < 4; ++cls) {
             const unsigned cell = c0 - ((cls & 1) ? 1u : 0u) - ((cls & 2) ? wp1 : 0u);
+            TMVS_ASSERT(cell < ncell);
             const uint4 pr = __ldg(par_d + cell);
             unsigned *v = ids[cls];
             v[0] = pr.x; v[1] = pr.y; v[2] = pr.z; v[3] = pr.w; v[4] = kEmptyId; v[5] = kEmptyId;
@@ -231,6 +234,7 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
                 if (id != kEmptyId) {
                     const unsigned px = id & 0xffffu, py = id >> 16;
                     const unsigned pix = py * (unsigned)W + px;
+                    TMVS_ASSERT(px < (unsigned)W && py < (unsigned)H);
                     const float2 c = __ldg(pos_d + pix);
                     const float gw = __ldg(g_d + pix) * inv_c;
                     const float wx = (cls & 1) ? __fsub_rn(c.x, qxf - 1.0f) : __fsub_rn(qxf + 1.0f, c.x);
