@@ -459,7 +459,7 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.gbox = ws.bbox + align256((size_t)n_src * B * n_tiles * D * 16);
     const size_t n_groups = (size_t)(((W + kTX - 1) / kTX + kGroup - 1) / kGroup) * (((H + kTY - 1) / kTY + kGroup - 1) / kGroup);
     ws.flags = ws.gbox + align256((size_t)n_src * B * n_groups * 16);
-    ws.tables = ws.flags + align256((size_t)(3 + n_tiles) * n_src * B * sizeof(int));
+    ws.tables = ws.flags + align256((size_t)(4 + n_tiles) * n_src * B * sizeof(int));
     ws.cells = H <= 32767 && W <= 65535;
     const size_t per_pair = tmvs_bwd_cells_bytes_per_pair(D, H, W);
     const int b_group = B < TMVS_GEOM_SLOTS / n_src ? B : TMVS_GEOM_SLOTS / n_src;
@@ -537,7 +537,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     int4 *bbox = (int4 *)(wsp + ws.bbox);
     int4 *gbox = (int4 *)(wsp + ws.gbox);
     int *flags = (int *)(wsp + ws.flags);
-    int *overflow = flags + 2 * (size_t)n_src * B;       // one per (view, batch) pair: some tile of it needs the tile scan
+    int *overflow = flags + 3 * (size_t)n_src * B;       // one per (view, batch) pair: some tile of it needs the tile scan
     int *tile_overflow = overflow + (size_t)n_src * B;   // one per (pair, 32x8 source tile): that tile needs the tile scan
     // TMVS_BWD_SRC_PATH=scan forces the tile-scan kernels (the robust path the cell tables fall back to)
     const char *src_path = getenv("TMVS_BWD_SRC_PATH");
@@ -550,7 +550,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, stream);
         if (rc != TMVS_OK) return rc;
         if (use_cells) {
-            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(3 + n_tiles) * n_src * B * sizeof(int), st);
+            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(4 + n_tiles) * n_src * B * sizeof(int), st);
             if (e != cudaSuccess) return (int)e;
         }
     }
@@ -568,7 +568,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         if (use_cells) {
             // grad_src through the cell tables; the tile-scan kernels below then run only if a cell overflowed
             rc = tmvs_bwd_src_cells((const float4 *)refp, depth, per_pixel, grad_views, grad_src, wsp + ws.tables,
-                                    ws.pairs_per_pass, flags + 2 * (size_t)n_src * b0, overflow + (size_t)n_src * b0,
+                                    ws.pairs_per_pass, flags + 3 * (size_t)n_src * b0, overflow + (size_t)n_src * b0,
                                     tile_overflow + (size_t)n_src * b0 * n_tiles, B, b0, bc, n_src, C, D,
                                     H, W, geom, st);
             if (rc != TMVS_OK) return rc;

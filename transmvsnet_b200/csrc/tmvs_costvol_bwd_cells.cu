@@ -30,13 +30,16 @@ namespace {
 
 constexpr int kTX = 32, kTY = 8;
 constexpr int kRegDC = 8;                       // planes per thread in the register / fix-up kernels
+constexpr int kListCap = 128;                   // losers a register CTA (256 pixels x 8 planes) can list; more -> full pass
 constexpr unsigned kEmptyId = 0xffffffffu;      // memset(0xff); ids are (y << 16 | x) < 2^31 (H <= 32767)
 
 struct CellTables {
     uint4 *par;         // [nvb][D][ncell]  parity slots (x&1 | (y&1)<<1)
     uint2 *ovf;         // [nvb][D][ncell]  overflow slots 1, 2
     float2 *pos;        // [nvb][D][HW]     sample position (ix, iy) of (p, d)
-    int *flags;         // [0] losers after the parity level, [1] losers after overflow slot 1
+    int *flags;         // [0] losers after the parity level, [1] losers after overflow slot 1, [2] some CTA's loser list overflowed
+    uint2 *list;        // [register CTA][kListCap] losers of the parity level: (pixel, plane | pair << 16)
+    int *list_count;    // [register CTA]
     int *overflow;      // [pair z of the launch group] raised when a footprint of that (view, batch) pair found no slot
     int *tile_overflow; // [pair z][32x8 source tile]: the tiles such a footprint touches -- the caller's tile-scan fallback
                         // redoes exactly those tiles, the gather below skips them
@@ -89,16 +92,22 @@ __global__ void __launch_bounds__(kTX * kTY)
 cells_fixup_kernel(CellTables tb, int z0, int D, int H, int W, int n_dchunks)
 {
     if (LEVEL >= 2 && tb.flags[LEVEL - 2] == 0) return;      // the level before had no loser: nothing to move
+    if (LEVEL == 2 && tb.flags[2] == 0) return;              // every CTA's losers fit its list: cells_fixup_list_kernel did it
+    if (LEVEL == 2 && tb.list_count[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] != -1)
+        return;                                              // this CTA's did
+    __shared__ unsigned warp_cnt[kTY];
     const int x = blockIdx.x * kTX + threadIdx.x, y = blockIdx.y * kTY + threadIdx.y;
-    if (x >= W || y >= H) return;
+    const bool valid = x < W && y < H;
     const int zl = blockIdx.z / n_dchunks, chunk = blockIdx.z - zl * n_dchunks;
     const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
     const size_t ncell = (size_t)(H + 1) * (W + 1);
     const TmvsDims dims = tmvs_dims(H, W, 0);               // footprint only: the arithmetic mode plays no part
     const unsigned id = ((unsigned)y << 16) | (unsigned)x;
     const int cls = (x & 1) | ((y & 1) << 1);
-    const int d1 = min(D, (chunk + 1) * kRegDC);
-    for (int d = chunk * kRegDC; d < d1; ++d) {
+    const int d_first = chunk * kRegDC;
+    const int d1 = min(D, d_first + kRegDC);
+    unsigned lost = 0;                                       // LEVEL 1: planes of this chunk where the pixel lost its slot
+    for (int d = d_first; valid && d < d1; ++d) {
         const size_t plane = (size_t)zl * D + d;
         const float2 c = tb.pos[plane * HW + pix];
         const TmvsTaps t = tmvs_footprint(c.x, c.y, dims);
@@ -109,6 +118,7 @@ cells_fixup_kernel(CellTables tb, int z0, int D, int H, int W, int n_dchunks)
         if (LEVEL == 1) {
             st_relaxed_u32(&tb.ovf[cell].x, id);
             st_relaxed_u32(reinterpret_cast<unsigned *>(tb.flags), 1u);
+            lost |= 1u << (d - d_first);
             continue;
         }
         if (tb.ovf[cell].x == id) continue;
@@ -128,6 +138,66 @@ cells_fixup_kernel(CellTables tb, int z0, int D, int H, int W, int n_dchunks)
             st_relaxed_u32(reinterpret_cast<unsigned *>(tf + yb * tb.n_tx + xa), 1u);
             st_relaxed_u32(reinterpret_cast<unsigned *>(tf + yb * tb.n_tx + xb), 1u);
         }
+    }
+    if (LEVEL == 1) {
+        // the losers of this CTA, compacted in (thread, plane) order into its list: the next level then visits only them
+        const unsigned mine = __popc(lost);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
+        }
+        if (threadIdx.x == 31) warp_cnt[threadIdx.y] = incl;
+        __syncthreads();
+        unsigned before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kTY; ++w) {
+            const unsigned c = warp_cnt[w];
+            if (w < (int)threadIdx.y) before += c;
+            total += c;
+        }
+        const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        if (total > (unsigned)kListCap) {
+            if (threadIdx.x == 0 && threadIdx.y == 0) {
+                tb.list_count[cta] = -1;                                            // too many: level 2 revisits
+                st_relaxed_u32(reinterpret_cast<unsigned *>(tb.flags + 2), 1u);     // this CTA's pixels in full
+            }
+        } else {
+            if (threadIdx.x == 0 && threadIdx.y == 0) tb.list_count[cta] = (int)total;
+            unsigned k = before + incl - mine;
+            uint2 *out = tb.list + (size_t)cta * kListCap;
+            while (lost) {
+                const int j = __ffs(lost) - 1;
+                lost &= lost - 1;
+                out[k++] = make_uint2((unsigned)pix, (unsigned)(d_first + j) | ((unsigned)zl << 16));
+            }
+        }
+    }
+}
+
+// Level 2 over the loser lists: losers of overflow slot 1 move to slot 2.
+__global__ void __launch_bounds__(128)
+cells_fixup_list_kernel(CellTables tb, int D, int H, int W)
+{
+    if (tb.flags[0] == 0) return;                            // no loser at all
+    const int n = tb.list_count[blockIdx.x];                 // -1: listed too many, the full-pass kernel revisits that CTA
+    const size_t HW = (size_t)H * W;
+    const size_t ncell = (size_t)(H + 1) * (W + 1);
+    const TmvsDims dims = tmvs_dims(H, W, 0);
+    const uint2 *in = tb.list + (size_t)blockIdx.x * kListCap;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const uint2 ent = in[e];
+        const unsigned pix = ent.x, d = ent.y & 0xffffu, zl = ent.y >> 16;
+        const unsigned y = pix / (unsigned)W, x = pix - y * (unsigned)W;
+        const size_t plane = (size_t)zl * D + d;
+        const float2 c = tb.pos[plane * HW + pix];
+        const TmvsTaps t = tmvs_footprint(c.x, c.y, dims);
+        const size_t cell = plane * ncell + cell_of(t, W);
+        const unsigned id = (y << 16) | x;
+        if (tb.ovf[cell].x == id) continue;
+        st_relaxed_u32(&tb.ovf[cell].y, id);
+        st_relaxed_u32(reinterpret_cast<unsigned *>(tb.flags + 1), 1u);
     }
 }
 
@@ -279,12 +349,14 @@ inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 size_t tmvs_bwd_cells_bytes_per_pair(int D, int H, int W)
 {
     const size_t ncell = (size_t)(H + 1) * (W + 1), HW = (size_t)H * W;
-    return align256((size_t)D * ncell * (sizeof(uint4) + sizeof(uint2))) + align256((size_t)D * HW * sizeof(float2));
+    const size_t ctas = (size_t)((W + kTX - 1) / kTX) * ((H + kTY - 1) / kTY) * ((D + kRegDC - 1) / kRegDC);
+    return align256((size_t)D * ncell * (sizeof(uint4) + sizeof(uint2))) + align256((size_t)D * HW * sizeof(float2)) +
+           align256(ctas * kListCap * sizeof(uint2)) + align256(ctas * sizeof(int)) + 256;   // + the loser lists and their counts
 }
 
 // grad_src of the (view, batch) pairs z = 0 .. n_src*bc-1 of one launch group (geom.rt[z], z = view * bc + bl),
 // `pairs_per_pass` pairs at a time through the table workspace `tables` (pairs_per_pass * bytes_per_pair bytes).
-// flags: 2 ints per pass; overflow: one int per pair of the group; tile_overflow: one int per (pair, 32x8 source tile)
+// flags: 3 ints per pass; overflow: one int per pair of the group; tile_overflow: one int per (pair, 32x8 source tile)
 // -- all zeroed by the caller.
 int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, const float *G, float *grad_src,
                        char *tables, int pairs_per_pass, int *flags, int *overflow, int *tile_overflow, int b_total,
@@ -306,7 +378,12 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         tb.par = reinterpret_cast<uint4 *>(tables);
         tb.ovf = reinterpret_cast<uint2 *>(tables + (size_t)nz * D * ncell * sizeof(uint4));
         tb.pos = reinterpret_cast<float2 *>(tables + (size_t)pairs_per_pass * cell_bytes);
-        tb.flags = flags + 2 * pass;
+        const size_t pos_bytes = align256((size_t)D * HW * sizeof(float2));
+        const size_t n_ctas = (size_t)n_tx * n_ty * n_dchunks * nz;
+        tb.list = reinterpret_cast<uint2 *>(tables + (size_t)pairs_per_pass * (cell_bytes + pos_bytes));
+        tb.list_count = reinterpret_cast<int *>(tables + (size_t)pairs_per_pass * (cell_bytes + pos_bytes) +
+                                                align256(n_ctas * kListCap * sizeof(uint2)));
+        tb.flags = flags + 3 * pass;
         tb.overflow = overflow;
         tb.tile_overflow = tile_overflow;
         tb.n_tx = n_tx;
@@ -319,7 +396,8 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         else
             cells_register_kernel<false><<<grid_pd, block, 0, st>>>(depth, tb, z0, b_first, bc, D, H, W, n_dchunks, geom);
         cells_fixup_kernel<1><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);
-        cells_fixup_kernel<2><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);
+        cells_fixup_list_kernel<<<(unsigned)n_ctas, 128, 0, st>>>(tb, D, H, W);          // level 2 over the loser lists ...
+        cells_fixup_kernel<2><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);    // ... or in full if one overflowed
         cells_fixup_kernel<3><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);
         dim3 grid_q(n_tx, n_ty, nz);
 #define TMVS_GATHER(C4T, EX)                                                                                        \
