@@ -12,13 +12,16 @@
 //                surface folds over, so in the common case every footprint owns its slot after one plain store.
 //   2. fix-up    (p, d) pairs that lost their slot to another pixel of the same parity (detected by reading the slot
 //                back in the next kernel -- the kernel boundary is the only synchronisation) move to overflow slot
-//                1, the losers of that to overflow slot 2; whoever is still homeless flags the 32x8 source tiles its
-//                footprint touches, and exactly those tiles are redone by the tile-scan kernels of tmvs_costvol_bwd.cu (bwd_src_kernel), which
-//                handle any multiplicity.  Each fix-up kernel returns at once when the level before it had no loser.
+//                1 and are listed, compacted per CTA; the next level walks the lists and moves the losers of slot 1
+//                to overflow slot 2; whoever is still homeless flags the 32x8 source tiles its footprint touches,
+//                and exactly those tiles are redone by the tile-scan kernels of tmvs_costvol_bwd.cu
+//                (bwd_src_kernel), which handle any multiplicity.  Each level returns at once when the level before
+//                it had no loser.
 //   3. gather    one thread OWNS one source pixel q of one view: for d = 0..D-1, for the four tap classes
 //                (nw, ne, sw, se), it reads the cell whose footprints hit q with that tap, sorts the <= 6 ids, and
-//                accumulates k * ref[:, p] in (plane, rank of the id within its cell, class) order from pos[d][p], G[d][p] and the packed
-//                reference features.  WHICH thread wins a slot never matters: the gather orders ids itself.
+//                accumulates k * ref[:, p] in (plane, rank of the id within its cell, class) order from pos[d][p],
+//                G[d][p] and the packed reference features.  WHICH thread wins a slot never matters: the gather
+//                orders ids itself.
 //
 // Work is O(voxel-views) with no barrier and no re-projection per overlapping tile (the tile-scan kernel re-projects
 // every (tile, plane) once per source tile its box overlaps, 4-6x, between block-wide barriers).
