@@ -190,7 +190,16 @@ def run_tmvs_arm(args, workload):
     sink = None
     if use_peer:
         h3, w3 = host[-1].depth_values.shape[2:]
-        sink = sharding.PeerMapSink(2 * world, (h3, w3), dev, dst=0)
+        ok = torch.ones(1, device=dev)
+        try:
+            sink = sharding.PeerMapSink(2 * world, (h3, w3), dev, dst=0, sync=False)
+        except Exception as e:      # no peer access between these GPUs: every rank falls back to the NCCL transport
+            print(f"[bench] rank {rank}: peer-mapped gather unavailable ({e}); using NCCL all_gather", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            sink, use_peer = None, False
+            comm = torch.cuda.Stream()
     step_no = [0]
 
     def step():

@@ -74,7 +74,7 @@ class PeerMapSink:
     before rank `dst` reads `result()`.  gather_maps (NCCL / gloo all_gather) remains the transport across boxes.
     """
 
-    def __init__(self, slots: int, hw, device, dst: int = 0, group=None):
+    def __init__(self, slots: int, hw, device, dst: int = 0, group=None, sync: bool = True):
         import ctypes
         from . import _lib
         lib = _lib.load()
@@ -91,10 +91,12 @@ class PeerMapSink:
         with torch.cuda.device(self.device):
             if self._owner:
                 handle = (ctypes.c_ubyte * 64)()
-                _lib.check(lib.tmvs_peer_buffer_create(nbytes, ctypes.byref(self._ptr), handle), "tmvs_peer_buffer_create")
-                payload = [bytes(handle)]
+                rc = lib.tmvs_peer_buffer_create(nbytes, ctypes.byref(self._ptr), handle)
+                payload = [bytes(handle) if rc == 0 else rc]          # the broadcast happens either way: nobody hangs
             if self.world > 1:
                 dist.broadcast_object_list(payload, src=dst, group=group)
+            if not isinstance(payload[0], bytes):
+                raise _lib.TmvsError(f"tmvs_peer_buffer_create failed on rank {dst} (code {payload[0]})")
             if not self._owner:
                 handle = (ctypes.c_ubyte * 64).from_buffer_copy(payload[0])
                 _lib.check(lib.tmvs_peer_buffer_open(handle, ctypes.byref(self._ptr)), "tmvs_peer_buffer_open")
@@ -102,7 +104,7 @@ class PeerMapSink:
             self.buffer = torch.as_tensor(_RawCuda(self._ptr.value, shape))
             if self.buffer.data_ptr() != self._ptr.value:
                 raise RuntimeError("PeerMapSink: torch copied the peer buffer instead of aliasing it")
-        if self.world > 1:
+        if self.world > 1 and sync:      # sync=False: the caller follows with its own collective (e.g. to agree on a fallback)
             dist.barrier(group=group)
 
     def slot(self, index: int) -> torch.Tensor:
