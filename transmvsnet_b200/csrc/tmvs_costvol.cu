@@ -215,7 +215,26 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
                 int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsFwdConst &kc,
                 const TmvsGeom &geom)
 {
+    // Shared-memory carveout: just what the resident CTAs need (accumulators + 1 KB per CTA the system reserves), so the
+    // rest of the unified 228 KB serves as L1 for the tap gather.  Measured (scripts/tune_costvol.py, TMVS_CARVEOUT_PCT):
+    // 0.699 -> 0.683 ms and 0.388 -> 0.379 ms for stages 2 / 3 against the driver's default; too small a carveout costs
+    // occupancy (8 % at stage 3: 0.457 ms), a large one costs hit rate (50 %: 0.73 / 0.40 ms).
+#ifdef TMVS_CARVEOUT_PCT      /* tuning override: one percentage for every kernel */
+#define TMVS_CARVEOUT(A) (TMVS_CARVEOUT_PCT)
+#else
+#define TMVS_CARVEOUT(A) ((MinBlocks<C4T>::value * (8 / TMVS_TILE_Y) * ((A) ? kDC * kTileX * kTileY * 4 + 1024 : 2048) * 100 + 228 * 1024 - 1) / (228 * 1024))
+#endif
+#define TMVS_SET_CARVEOUT(V, A)                                                                              \
+    {                                                                                                        \
+        static bool once = false;                                                                            \
+        if (!once) {                                                                                         \
+            cudaFuncSetAttribute(costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP>,                     \
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_CARVEOUT(A));          \
+            once = true;                                                                                     \
+        }                                                                                                    \
+    }
 #define TMVS_LAUNCH(V, A)                                                                                    \
+    TMVS_SET_CARVEOUT(V, A)                                                                                  \
     costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP><<<grid, block, 0, st>>>(                          \
         ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,      \
         W, n_src, n_dchunks, kc, geom)
