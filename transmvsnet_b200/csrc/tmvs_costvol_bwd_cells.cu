@@ -403,15 +403,21 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         cells_fixup_kernel<2><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);    // ... or in full if one overflowed
         cells_fixup_kernel<3><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);
         dim3 grid_q(n_tx, n_ty, nz);
+#ifdef TMVS_BWD_CARVEOUT
+#define TMVS_GATHER_ATTR(C4T, EX) cudaFuncSetAttribute(cells_gather_kernel<C4T, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_BWD_CARVEOUT);
+#else
+#define TMVS_GATHER_ATTR(C4T, EX)
+#endif
 #define TMVS_GATHER(C4T, EX)                                                                                        \
+        TMVS_GATHER_ATTR(C4T, EX)                                                                                   \
         cells_gather_kernel<C4T, EX><<<grid_q, block, 0, st>>>(refp, G, tb, grad_src, z0, b_total, b_first, bc, C, c4, \
                                                                D, H, W)
-        if (c4 == 2) TMVS_GATHER(2, true);
-        else if (c4 == 4) TMVS_GATHER(4, true);
-        else if (c4 == 8) TMVS_GATHER(8, true);
-        else if (c4 < 4) TMVS_GATHER(4, false);
-        else if (c4 < 8) TMVS_GATHER(8, false);
-        else TMVS_GATHER(16, false);
+        if (c4 == 2) { TMVS_GATHER(2, true); }
+        else if (c4 == 4) { TMVS_GATHER(4, true); }
+        else if (c4 == 8) { TMVS_GATHER(8, true); }
+        else if (c4 < 4) { TMVS_GATHER(4, false); }
+        else if (c4 < 8) { TMVS_GATHER(8, false); }
+        else { TMVS_GATHER(16, false); }
 #undef TMVS_GATHER
         const int rc = tmvs_launch_status();
         if (rc != TMVS_OK) return rc;
