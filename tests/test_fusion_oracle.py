@@ -60,3 +60,17 @@ def test_oracle_texture_model_at_texel_centres_and_edges():
     assert np.allclose(mid, 0.5 * (img[0, 0] + img[0, 1]), atol=1e-7)
     edge = oracle.tex_linear(img, np.array([[0.0, 0.0], [8.0, 6.0]], np.float32))              # clamp to edge
     assert np.allclose(edge[0], img[0, 0]) and np.allclose(edge[1], img[5, 7])
+
+
+def test_images_from_bgra_follows_main_cpp():
+    """main.cpp:128-141: colour / 255, depth = 425 + 512 * (alpha / 255); the 8-bit alpha written by finalize_maps
+    (utils.py:11-21) therefore decodes to 2 mm steps of the 425-935 mm range."""
+    import torch
+    bgra = torch.zeros(1, 2, 3, 4, dtype=torch.uint8)
+    bgra[0, 0, 0] = torch.tensor([255, 128, 0, 0], dtype=torch.uint8)
+    bgra[0, 1, 2] = torch.tensor([1, 2, 3, 255], dtype=torch.uint8)
+    img = fusion.images_from_bgra(bgra)
+    assert img.dtype == torch.float32 and tuple(img.shape) == (1, 2, 3, 4)
+    assert float(img[0, 0, 0, 0]) == 1.0 and abs(float(img[0, 0, 0, 1]) - 128 / 255) < 1e-7
+    assert float(img[0, 0, 0, 3]) == 425.0 and float(img[0, 1, 2, 3]) == 937.0
+    assert float(img[0, 0, 1, 3]) == 425.0                    # alpha 0 -> below fusibile's 425.001 floor: skipped
