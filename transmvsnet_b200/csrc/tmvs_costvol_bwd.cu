@@ -483,15 +483,9 @@ int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st,
     dim3 block(kTX, kTY);
     const int n_ty = n_tiles / n_tx;
     const int n_gx = (n_tx + kGroup - 1) / kGroup, n_gy = (n_ty + kGroup - 1) / kGroup, n_groups = n_gx * n_gy;
-#ifdef TMVS_BWD_CARVEOUT
-#define TMVS_REF_ATTR(C4T, EX) cudaFuncSetAttribute(bwd_ref_kernel<C4T, EX, PER_PIXEL>, cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_BWD_CARVEOUT);
-#else
-#define TMVS_REF_ATTR(C4T, EX)
-#endif
 #define TMVS_BWD(C4T, EX)                                                                                          \
     do {                                                                                                           \
         if (want_ref) {                                                                                            \
-            TMVS_REF_ATTR(C4T, EX)                                                                                 \
             bwd_ref_kernel<C4T, EX, PER_PIXEL><<<grid, block, 0, st>>>(packed, depth, G, partial, b_total, b_first, \
                                                                        b_chunk, C, c4, D, H, W, geom);             \
         }                                                                                                          \

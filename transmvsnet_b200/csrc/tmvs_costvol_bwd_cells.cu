@@ -403,13 +403,7 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         cells_fixup_kernel<2><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);    // ... or in full if one overflowed
         cells_fixup_kernel<3><<<grid_pd, block, 0, st>>>(tb, z0, D, H, W, n_dchunks);
         dim3 grid_q(n_tx, n_ty, nz);
-#ifdef TMVS_BWD_CARVEOUT
-#define TMVS_GATHER_ATTR(C4T, EX) cudaFuncSetAttribute(cells_gather_kernel<C4T, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_BWD_CARVEOUT);
-#else
-#define TMVS_GATHER_ATTR(C4T, EX)
-#endif
 #define TMVS_GATHER(C4T, EX)                                                                                        \
-        TMVS_GATHER_ATTR(C4T, EX)                                                                                   \
         cells_gather_kernel<C4T, EX><<<grid_q, block, 0, st>>>(refp, G, tb, grad_src, z0, b_total, b_first, bc, C, c4, \
                                                                D, H, W)
         if (c4 == 2) { TMVS_GATHER(2, true); }
