@@ -225,12 +225,14 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
 #define TMVS_CARVEOUT(A) ((MinBlocks<C4T>::value * (8 / TMVS_TILE_Y) * ((A) ? kDC * kTileX * kTileY * 4 + 1024 : 2048) * 100 + 228 * 1024 - 1) / (228 * 1024))
 #endif
 #define TMVS_SET_CARVEOUT(V, A)                                                                              \
-    {                                                                                                        \
-        static bool once = false;                                                                            \
-        if (!once) {                                                                                         \
+    {   /* a function attribute is per device: set it once for each device this process launches on */       \
+        static bool done[64] = {};                                                                           \
+        int dev_id = 0;                                                                                      \
+        cudaGetDevice(&dev_id);                                                                              \
+        if (dev_id < 0 || dev_id >= 64 || !done[dev_id]) {                                                   \
             cudaFuncSetAttribute(costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP>,                     \
                                  cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_CARVEOUT(A));          \
-            once = true;                                                                                     \
+            if (dev_id >= 0 && dev_id < 64) done[dev_id] = true;                                             \
         }                                                                                                    \
     }
 #define TMVS_LAUNCH(V, A)                                                                                    \
