@@ -32,6 +32,25 @@ def test_homo_warping_golden(name):
     assert np.array_equal(out.cpu().numpy() == 0, g["out"] == 0)       # zero padding / z<1e-6 exactly
 
 
+def test_pack_tma_and_register_transpose_paths_agree(monkeypatch):
+    """The layout pre-pass has a TMA-engine kernel (contiguous NCHW, C in {8,16,32,64}, W % 4 == 0) and the
+    register-transpose kernels it falls back to: identical packed features wherever a pixel exists (the padding pixels
+    of a row's last 8-pixel block are never read)."""
+    torch.manual_seed(4)
+    for b, c, h, w in ((1, 32, 24, 64), (2, 16, 17, 100), (1, 8, 9, 132), (2, 64, 5, 8), (1, 32, 288, 400)):
+        feats = [torch.randn(b, c, h, w, device=DEV) for _ in range(3)]
+        monkeypatch.setenv("TMVS_PACK_PATH", "ldg")
+        ref = ops.pack_sources(feats)
+        monkeypatch.delenv("TMVS_PACK_PATH", raising=False)
+        got = ops.pack_sources(feats)                           # [N,B,H,Wb,C4,8,4]
+        valid = (torch.arange(ref.shape[3], device=DEV)[:, None] * 8 + torch.arange(8, device=DEV)[None, :]) < w
+        m = valid[None, None, None, :, None, :, None].expand_as(ref)
+        assert torch.equal(got[m], ref[m]), (b, c, h, w)
+        # and back to NCHW: channel 4g+k of pixel 8*blk+j
+        nchw = got.permute(0, 1, 4, 6, 2, 3, 5).reshape(3, b, c, h, ref.shape[3] * 8)[..., :w]
+        assert torch.equal(nchw, torch.stack(feats, 0))
+
+
 def test_homo_warping_refuses_to_drop_gradients():
     g = golden(WARP_CASES[0])
     src = cu(g["src"]).requires_grad_(True)

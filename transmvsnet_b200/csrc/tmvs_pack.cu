@@ -7,7 +7,14 @@
 //
 // tmvs_homo_warp_fwd: models/module.py:284-322 for one view, materialising [B][C][D][H][W]
 // (the reference's own interface; the fused kernels in tmvs_costvol.cu never form this volume).
+#include <stdlib.h>
+#include <string.h>
+
 #include "tmvs_common.cuh"
+
+// TMA-engine variant (tmvs_pack_tma.cu); TMVS_E_UNSUPPORTED when it does not apply
+int tmvs_pack_sources_tma(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
+                          float *packed, int B, int C, int H, int W, cudaStream_t st);
 
 namespace {
 
@@ -186,6 +193,12 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
     bool aligned = true;
     for (int i = 0; i < n_src; ++i) aligned = aligned && (((uintptr_t)src[i] & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    // contiguous NCHW maps go through the TMA engine (TMVS_PACK_PATH=ldg keeps the register-transpose kernel)
+    const char *pack_path = getenv("TMVS_PACK_PATH");
+    if (!(pack_path && strcmp(pack_path, "ldg") == 0)) {
+        const int rc = tmvs_pack_sources_tma(src, n_src, sB, sC, sH, sW, packed, B, C, H, W, st);
+        if (rc != TMVS_E_UNSUPPORTED) return rc;
+    }
     // (a whole-line variant -- 8 pixels per thread -- measured ~8 % slower on B200 and was dropped; two channel
     //  groups per thread and 128-thread CTAs measured 13 % faster: scripts/tune_pack.py)
     if (aligned && sW == 1 && (W & 3) == 0 && (sH & 3) == 0 && (sC & 3) == 0 && (sB & 3) == 0) {
