@@ -64,7 +64,8 @@ HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1ELb0E", "costvol_fwd_kerne
                "softmax_wta_kernelILi32E", "softmax_wta_kernelILi8E", "depth_wta_kernel",
                "bwd_src_kernelILi8ELb1ELb1E", "bwd_ref_kernelILi8ELb1ELb1E", "bwd_bbox_kernelILb1E",
                "costvol_tma_kernelILi4ELb1ELb0ELb1E", "cells_register_kernelILb1E", "cells_fixup_kernelILi1E",
-               "cells_gather_kernelILi4ELb1E", "fuse_points_kernel", "pixelwise_weight_kernel")
+               "cells_gather_kernelILi4ELb1E", "fuse_points_kernel", "pixelwise_weight_kernel", "pack_sources_tma_kernelILi8E",
+               "softmax_wta_split_lean_kernelILi4ELi8ELb1E", "softmax_wta_lean_kernelILi8ELb1E")
 
 
 def dump_sass(out_dir: str) -> None:
