@@ -3,8 +3,8 @@
 //
 // The register-transpose kernel (tmvs_pack.cu pack_sources_nchw4_kernel) issues one 128-bit load per channel plane
 // and thread and is throttled by the LSU queue (ncu: lg_throttle 20 per issue at 3.4-4.5 TB/s).  Here one elected
-// thread per CTA asks the TMA engine for a [C planes][1 row][64 pixels] box (cp.async.bulk.tensor.3d, completion on an
-// mbarrier): the loads never enter the LSU queue, and the CTA only does the transposing half -- conflict-free
+// thread per CTA asks the TMA engine for an 8 KB box of [C planes][1 row][64-256 pixels] (cp.async.bulk.tensor.3d,
+// completion on an mbarrier): the loads never enter the LSU queue, and the CTA only does the transposing half -- conflict-free
 // shared-memory reads (a warp = 32 x-adjacent pixels of one channel group) and fully coalesced 128-bit stores
 // (4 x 128 contiguous bytes per warp).  Applies to contiguous NCHW maps with W % 4 == 0 and C % 4 == 0 (what
 // FeatureNet / FMT produce, models/module.py:399-422); anything else takes the kernels of tmvs_pack.cu.
@@ -12,9 +12,17 @@
 
 #include "tmvs_common.cuh"
 
+#ifndef TMVS_PACK_PX16
+#define TMVS_PACK_PX16 128
+#endif
+#ifndef TMVS_PACK_PX8
+#define TMVS_PACK_PX8 256
+#endif
+
 namespace {
 
-constexpr int kPX = 64;          // pixels per box
+// pixels per box: 8 KB boxes (C x PX x 4 bytes), at most 256 pixels (the TMA box limit per dimension)
+template <int C4T> struct BoxPx { static constexpr int value = C4T >= 8 ? 64 : (C4T == 4 ? TMVS_PACK_PX16 : TMVS_PACK_PX8); };
 constexpr int kThreads = 128;
 
 struct PackMaps {
@@ -28,6 +36,7 @@ __global__ void __launch_bounds__(kThreads)
 pack_sources_tma_kernel(const __grid_constant__ PackMaps maps, float4 *__restrict__ packed, int B, int H, int W)
 {
     constexpr int C = 4 * C4T;
+    constexpr int kPX = BoxPx<C4T>::value;
     __shared__ __align__(128) float tile[C][kPX];
     __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x;
@@ -41,7 +50,7 @@ pack_sources_tma_kernel(const __grid_constant__ PackMaps maps, float4 *__restric
     if (tid == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)),
                      "r"((unsigned)(C * kPX * sizeof(float))) : "memory");
-        // box {64 px, 1 row, C planes} at (x0, y, b * C); pixels beyond W are zero-filled by the engine
+        // box {kPX pixels, 1 row, C planes} at (x0, y, b * C); pixels beyond W are zero-filled by the engine
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
             ::"r"(smem_u32(&tile[0][0])), "l"(&maps.m[view]), "r"(smem_u32(&bar)), "r"(x0), "r"(y), "r"(b * C) : "memory");
@@ -112,13 +121,15 @@ int tmvs_pack_sources_tma(const float *const *src, int n_src, int64_t sB, int64_
         if (((uintptr_t)src[i] & 15) != 0) return TMVS_E_UNSUPPORTED;
         const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * C};
         const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)kPX, 1u, (cuuint32_t)C};
+        const int px = C == 8 ? BoxPx<2>::value : (C == 16 ? BoxPx<4>::value : 64);
+        const cuuint32_t box[3] = {(cuuint32_t)px, 1u, (cuuint32_t)C};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)src[i], gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return TMVS_E_UNSUPPORTED;
     }
+    const int kPX = C == 8 ? BoxPx<2>::value : (C == 16 ? BoxPx<4>::value : 64);
     dim3 grid((W + kPX - 1) / kPX, H, n_src * B);
     float4 *out = (float4 *)packed;
     switch (C) {
