@@ -10,8 +10,15 @@ BASELINE.json) and ms per reference view.  Under torchrun every rank processes i
 views (weak scaling, sharded by reference view) and the stage-3 depth/confidence maps are gathered
 on rank 0 over NCCL.
 
---impl reference times the reference's PyTorch CPU op sequence (oracle/torch_port.py: the reference is
-Python and /root/reference does not exist on the GPU box) on the host cores, on a bounded sample.
+--impl reference times the REFERENCE's own function for the path -- models.TransMVSNet.DepthNet.forward of the
+unmodified model package staged under oracle/_ref by build() (oracle/build.py; /root/reference does not exist on the
+GPU box) -- on the host cores at the SAME full-size configuration as the GPU arm: one step = the three DepthNet.forward
+calls of one reference view, with the stand-in 3-D CNN logits and the stage-1 view weights given, as in the GPU arm.
+The oracle port (oracle/torch_port.py) is only the fallback when oracle/_ref has not been staged.
+
+The e2e figure walks a whole scan (49 views, every view the reference view once, ring pairing) through
+HostPipeline.process_scan from pinned host memory; `workloads` carries the other BASELINE configs measured in the same
+run (T&T-shaped N=7 forward, BlendedMVS-shaped B=8 forward + backward, three corners of the D x C x N sweep).
 """
 from __future__ import annotations
 
@@ -44,7 +51,7 @@ WORKLOADS = {
     "bld": dict(height=576, width=768, n_views=7, kind="unit", batch=8,
                 name="BlendedMVS-shaped 576x768 N=7 B=8 D=48/32/8 fp32 forward"),
 }
-CPU_SAMPLE_DIV = 4      # the CPU arms run the same cascade on an image 1/4 x 1/4 the size (1/16 of the voxels)
+SCAN_VIEWS = 49         # views per scan in the e2e figure (DTU: 49 per scan, datasets/general_eval.py:25-57)
 
 
 def parse_args():
@@ -56,11 +63,22 @@ def parse_args():
     ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true")
+    ap.add_argument("--scan-views", type=int, default=SCAN_VIEWS)
     return ap.parse_args()
 
 
 def voxel_views(stages) -> int:
     return sum(s.voxel_views for s in stages)
+
+
+def make_config(workload: dict, vv: int, world: int, gather: str) -> dict:
+    """The `config` object of the JSON line -- the same for both arms (the reference arm times the same workload)."""
+    how = {"peer": ", depth+conf maps written by the read-out kernel into rank 0's buffer over NVLink peer memory",
+           "nccl": ", NCCL all_gather of depth+conf", "": ""}[gather if world > 1 else ""]
+    return {"workload": workload["name"], "voxel_views_per_step": vv,
+            "l2": "inputs larger than L2 (>= 1 GB touched per step)", "view_weights": "given as inputs",
+            "sharding": "by reference view, one process per GPU" + how}
 
 
 def algorithmic_bytes(st) -> dict:
@@ -70,7 +88,8 @@ def algorithmic_bytes(st) -> dict:
     c = st.features[0].shape[1]
     hw = h * w
     return {
-        # read Nsrc*C*h*w NCHW, write the same packed
+        # layout pre-pass (read Nsrc*C*h*w NCHW, write the same packed): the kernel's own traffic.  It is NOT part of
+        # SURVEY 8(d)'s algorithmic bytes of the path (those count the features once, in costvol_fwd below).
         "pack_sources": 4 * b * (2 * n_src * c * hw),
         # (1+Nsrc)*C*h*w features + D*h*w hypotheses + Nsrc*h*w weights in, D*h*w similarity out
         "costvol_fwd": 4 * b * ((1 + n_src) * c * hw + d * hw + n_src * hw + d * hw),
@@ -113,50 +132,179 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------- CPU arms
+class _GivenLogits:
+    """Stand-in for the 3-D CNN (`cost_regularization`, not part of the path): hands DepthNet.forward the same
+    precomputed logits the GPU arm's read-out kernel consumes."""
+
+    def __init__(self, logits):
+        self.logits = logits
+
+    def __call__(self, similarity):
+        return self.logits.unsqueeze(1)
+
+
 def cpu_hot_path_time(workload: dict, steps: int, warmup: int, min_seconds: float = 0.0):
-    """The reference's PyTorch CPU op sequence (oracle/torch_port.py) on a bounded sample of the workload.
-    Runs `steps` timed passes, then keeps going until `min_seconds` of timed CPU work have accumulated."""
+    """The reference's own DepthNet.forward (oracle/_ref, staged by build()) on the host cores at the FULL size of the
+    workload: one step = one reference view = the three stage calls.  Falls back to the oracle's port of the same ATen
+    op sequence (oracle/torch_port.py) when the reference has not been staged.  Runs `steps` timed passes, then keeps
+    going until `min_seconds` of timed CPU work have accumulated."""
     import torch
-    from oracle import torch_port
+    from oracle import build as oracle_build
     from transmvsnet_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    h, w = workload["height"] // CPU_SAMPLE_DIV, workload["width"] // CPU_SAMPLE_DIV
-    h, w = h // 4 * 4, w // 4 * 4
-    stages = synthetic.make_cascade(batch=1, n_views=workload["n_views"], height=h, width=w, kind=workload["kind"], seed=0)
+    stages = synthetic.make_cascade(batch=1, n_views=workload["n_views"], height=workload["height"], width=workload["width"],
+                                    kind=workload["kind"], seed=0)
     vv = voxel_views(stages)
-    with torch.no_grad():
-        for _ in range(warmup):
+    ref = oracle_build.import_reference()
+    if ref is not None:
+        kind = "reference"
+        net = ref[1].DepthNet().eval()                # PixelwiseNet parameters unused: the view weights are given
+
+        def one_pass():
+            for st in stages:
+                net(st.features, st.proj_matrix, st.depth_values, st.num_depth, _GivenLogits(st.logits),
+                    view_weights=st.view_weights)
+        what = "models.TransMVSNet.DepthNet.forward of the unmodified reference (oracle/_ref)"
+    else:
+        from oracle import torch_port
+        kind = "port"
+
+        def one_pass():
             for st in stages:
                 torch_port.hot_path(st)
+        what = "oracle/torch_port.py (the reference's ATen op sequence; oracle/_ref not staged)"
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_pass()
         times = []
         while len(times) < steps or sum(times) < min_seconds:
             t0 = time.perf_counter()
-            for st in stages:
-                torch_port.hot_path(st)
+            one_pass()
             times.append(time.perf_counter() - t0)
-    sample = (f"same cascade on a {h}x{w} image (1/{CPU_SAMPLE_DIV ** 2} of the voxels), N={workload['n_views']}, "
-              f"{vv / 1e6:.2f} M voxel-views per step, torch {torch.__version__} CPU ops, view weights given")
-    return vv, times, cores, sample
+    sample = (f"{what}, full size {workload['height']}x{workload['width']} N={workload['n_views']}, "
+              f"{vv / 1e6:.2f} M voxel-views per step (one reference view), torch {torch.__version__} CPU ops, "
+              f"view weights and logits given")
+    return vv, times, cores, sample, kind
 
 
 def run_reference_arm(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, args.warmup)   # exactly K timed steps; each is a bounded sample
-    vv, times, cores, sample = cpu_hot_path_time(workload, steps, warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)   # exactly K timed steps of the full-size workload
+    vv, times, cores, sample, kind = cpu_hot_path_time(workload, steps, warmup)
     total = sum(times)
     value = vv * len(times) / total
     line = {
         "impl": "reference", "metric": "cost_volume_voxel_views_per_s", "value": value, "unit": "voxel-views/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload["name"], "timed_sample": sample},
-        "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": make_config(workload, vv, args.gpus, "peer"),
+        "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxel-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+# ----------------------------------------------------------------------------------------- other BASELINE configs
+def _timed(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure_workloads(dev, rank: int, world: int):
+    """BASELINE.json configs 3-5 in the same run, a few steps each, on every rank's own data (weak scaling by
+    reference view / batch shard): max over ranks of the per-rank time, aggregate = world x per-rank work.
+      tnt   T&T-shaped 1056x1920 N=7 forward cascade (pack + cost volume + read-out, 3 stages)
+      bld   BlendedMVS-shaped 576x768 N=7 batch 8: forward cascade, and forward + backward of the cost volume through
+            torch.autograd (atomic-free grad_ref / grad_src kernels) per stage
+      sweep three corners of D x C x N at a 288x400 map
+      stage1_learned  DTU stage 1 as the cascade runs it at inference: per-view similarity -> folded PixelwiseNet ->
+            aggregation (SURVEY 8(d) asks for the with-PixelwiseNet figure separately)."""
+    import torch
+    import torch.distributed as dist
+    import transmvsnet_b200 as tm
+    from transmvsnet_b200 import ops, pipeline, synthetic
+
+    def agg_ms(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    out = {}
+    # ---- config 3
+    w = WORKLOADS["tnt"]
+    st = synthetic.make_cascade(batch=1, n_views=w["n_views"], height=w["height"], width=w["width"], kind=w["kind"], seed=rank)
+    ds = [pipeline.stage_to_device(x, dev) for x in st]
+    ms = agg_ms(_timed(lambda: pipeline.run_cascade(ds), 10))
+    vv = voxel_views(st)
+    out["tnt_forward"] = {"workload": w["name"], "ms_per_ref_view": round(ms, 4), "voxel_views_per_step": vv,
+                          "value": world * vv / (ms * 1e-3), "unit": "voxel-views/s", "n_gpus": world}
+    del ds, st
+    torch.cuda.empty_cache()
+    # ---- config 4
+    w = WORKLOADS["bld"]
+    st = synthetic.make_cascade(batch=w["batch"], n_views=w["n_views"], height=w["height"], width=w["width"], kind=w["kind"],
+                                seed=rank)
+    ds = [pipeline.stage_to_device(x, dev) for x in st]
+    ms_f = agg_ms(_timed(lambda: pipeline.run_cascade(ds), 5))
+
+    def fwd_bwd():
+        for d in ds:
+            fs = [f.detach().requires_grad_(True) for f in d["features"]]
+            agg, _ = ops.cost_volume(fs[0], fs[1:], d["rot_trans"], d["depth_values"], d["view_weights"])
+            agg.backward(torch.ones_like(agg))
+    ms_fb = agg_ms(_timed(fwd_bwd, 3, warm=1))
+    vv = voxel_views(st)
+    out["bld_forward"] = {"workload": w["name"], "ms_per_batch": round(ms_f, 4), "voxel_views_per_step": vv,
+                          "value": world * vv / (ms_f * 1e-3), "unit": "voxel-views/s", "n_gpus": world}
+    out["bld_forward_backward"] = {
+        "workload": "BlendedMVS-shaped 576x768 N=7 B=8: cost volume forward + backward wrt all feature maps through "
+                    "torch.autograd, 3 stages (grad of ones)", "ms_per_batch": round(ms_fb, 4),
+        "voxel_views_per_step": vv, "value": world * vv / (ms_fb * 1e-3), "unit": "voxel-views/s (forward count)",
+        "n_gpus": world}
+    del ds, st
+    torch.cuda.empty_cache()
+    # ---- config 5 (corners)
+    rows = []
+    for d_, c_, n_ in ((48, 8, 3), (96, 16, 5), (192, 32, 11)):
+        s1 = synthetic.make_stage(1, batch=1, n_views=n_, height=1152, width=1600, channels=c_, num_depth=d_, seed=rank)
+        d1 = pipeline.stage_to_device(s1, dev)
+        ms = agg_ms(_timed(lambda: pipeline.run_stage(d1), 10))
+        rows.append({"D": d_, "C": c_, "N": n_, "map": "288x400", "ms": round(ms, 4), "voxel_views": s1.voxel_views,
+                     "value": world * s1.voxel_views / (ms * 1e-3), "unit": "voxel-views/s", "n_gpus": world})
+        del d1, s1
+    out["sweep_corners"] = rows
+    torch.cuda.empty_cache()
+    # ---- DTU stage 1 with the view weights LEARNED (eval-mode PixelwiseNet folded, N2)
+    s1 = synthetic.make_stage(1, batch=1, n_views=5, height=1152, width=1600, seed=rank)
+    d1 = pipeline.stage_to_device(s1, dev)
+    net = tm.DepthNet().to(dev).eval()
+    ident = torch.nn.Identity()
+    pm = s1.proj_matrix
+
+    def learned():
+        with torch.no_grad():
+            net(d1["features"], pm, d1["depth_values"], s1.num_depth, ident, view_weights=None)
+    ms = agg_ms(_timed(learned, 10))
+    out["dtu_stage1_learned_weights"] = {
+        "what": "DepthNet.forward(view_weights=None), eval: pack + per-view similarity + folded PixelwiseNet + "
+                "aggregation + read-out (Identity in place of the 3-D CNN)", "ms": round(ms, 4),
+        "voxel_views": s1.voxel_views, "value": world * s1.voxel_views / (ms * 1e-3), "unit": "voxel-views/s"}
+    del d1, s1, net
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -307,21 +455,29 @@ def run_tmvs_arm(args, workload):
                 "frac": round(top["gbps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": top["ms"], "algorithmic_bytes": int(top["algorithmic_mb"] * 1e6),
                 "all_kernels": kernels, "sm_load_path": sm_load,
-                "step_algorithmic_frac": round(sum(k["algorithmic_mb"] for k in kernels) * 1e6 / 1e9 /
+                # SURVEY 8(d) bytes only: cost volume + read-out (the layout pre-pass is the kernels' own traffic)
+                "step_algorithmic_mb": round(sum(k["algorithmic_mb"] for k in kernels
+                                                 if not k["kernel"].startswith("pack_sources")), 2),
+                "step_algorithmic_frac": round(sum(k["algorithmic_mb"] for k in kernels
+                                                   if not k["kernel"].startswith("pack_sources")) * 1e6 / 1e9 /
                                                (elapsed_ms * 1e-3 / args.steps) / peak, 4)}
 
-    # ---- end to end through the public API: pinned host inputs, H2D + kernels + D2H every step
+    # ---- end to end through the public API: a whole scan from pinned host memory (H2D + kernels + D2H for every view)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and workload["batch"] == 1:
+        del dev_stages
+        torch.cuda.empty_cache()
+        scan = pipeline.pin_scan(synthetic.make_scan(args.scan_views, n_views=workload["n_views"], height=workload["height"],
+                                                     width=workload["width"], kind=workload["kind"], seed=rank))
         pipe = pipeline.HostPipeline(dev)
-        for _ in range(2):
-            pipe.process_view(host)
+        pipe.process_scan(scan)                              # warm-up scan: allocates the resident slots
         barrier()
-        k_e2e = max(1, min(args.steps, 20))
+        n_scans = max(1, round(args.steps / len(scan.jobs)))
         sampler.active.set()
+        barrier()
         e0.record()
-        for _ in range(k_e2e):
-            pipe.process_view(host)
+        for _ in range(n_scans):
+            pipe.process_scan(scan)
         e1.record()
         barrier()
         sampler.active.clear()
@@ -330,18 +486,28 @@ def run_tmvs_arm(args, workload):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        e2e = {"value": world * vv * k_e2e / (ms * 1e-3), "unit": "voxel-views/s",
-               "h2d_bytes_per_step": sum(pipeline.stage_h2d_bytes(s, n == 0) for n, s in enumerate(host)),
-               "h2d_what": "features + logits + stage-1 view weights + depth seeds; hypotheses generated on device",
-               "d2h_bytes_per_step": pipeline.HostPipeline.d2h_bytes(host), "steps": k_e2e,
-               "ms_per_step": ms / k_e2e}
+        k_e2e = n_scans * len(scan.jobs)
+        e2e = {"value": world * scan.voxel_views * n_scans / (ms * 1e-3), "unit": "voxel-views/s",
+               "h2d_bytes_per_step": pipe.h2d_bytes // len(scan.jobs),
+               "h2d_what": "per reference view, averaged over the scan: ONE new feature pyramid (each view crosses PCIe and "
+                           "is packed once per scan, then stays resident) + the stand-in 3-D CNN logits + stage-1 view "
+                           "weights + depth seeds; hypotheses generated on the device",
+               "d2h_bytes_per_step": pipeline.HostPipeline.d2h_bytes(scan.jobs[0]), "steps": k_e2e,
+               "ms_per_step": ms / k_e2e,
+               "scan": f"{len(scan.pyramids)} views, every view the reference view once, {workload['n_views'] - 1} source "
+                       f"views each (ring pairing), {n_scans} scan(s) timed after one warm-up scan; one scan per rank"}
+        del scan, pipe
+        torch.cuda.empty_cache()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    extra = None
+    if not args.no_workloads:
+        extra = measure_workloads(dev, rank, world)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cvv, times, cores, sample = cpu_hot_path_time(workload, steps=3, warmup=1, min_seconds=10.0)
-        cpu = {"value": cvv * len(times) / sum(times), "unit": "voxel-views/s", "cores": cores, "kind": "port",
+        cvv, times, cores, sample, kind = cpu_hot_path_time(workload, steps=2, warmup=1, min_seconds=10.0)
+        cpu = {"value": cvv * len(times) / sum(times), "unit": "voxel-views/s", "cores": cores, "kind": kind,
                "sample": sample + f"; {len(times)} passes, {sum(times):.1f} s of CPU work",
                "best_pass_value": cvv / min(times)}
 
@@ -351,12 +517,8 @@ def run_tmvs_arm(args, workload):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "ms_per_ref_view": elapsed_ms / args.steps / workload["batch"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload["name"], "voxel_views_per_step": vv,
-                       "l2": "inputs larger than L2 (>= 1 GB touched per step)", "view_weights": "given as inputs",
-                       "sharding": "by reference view, one process per GPU" + (
-                           ", depth+conf maps written by the read-out kernel into rank 0's buffer over NVLink peer memory"
-                           if use_peer else (", NCCL all_gather of depth+conf" if world > 1 else ""))},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": make_config(workload, vv, world, "peer" if use_peer else "nccl"),
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "workloads": extra,
             "clocks": sampler.summary(),
         }
         emit(line)

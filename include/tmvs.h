@@ -19,9 +19,10 @@
  *       [Nsrc][B][H][Wb][C4][8 px][4 ch],  C4 = ceil(C/4) (zero padded), Wb = ceil(W/8),
  *     produced by tmvs_pack_sources(): one bilinear tap of 4 channels is one 128-bit load, 8
  *     x-adjacent pixels share a 128-byte line and the C4 groups of a pixel are 128 bytes apart;
- *   - rot_trans is a HOST array [Nsrc][B][12]: 3x3 `rot` (row major) then `trans` of
+ *   - rot_trans is an array [Nsrc][B][12]: 3x3 `rot` (row major) then `trans` of
  *       proj = src_proj @ inverse(ref_proj)            (models/module.py:295-297),
- *     computed by the caller with the same torch ops as the reference;
+ *     computed by the caller with the same torch ops as the reference; on the HOST by default (passed to the
+ *     kernels by value) or, with TMVS_F_RT_DEVICE, on the device (read in place: no copy, no synchronisation);
  *   - depth hypotheses are [B][D] (per_pixel = 0) or [B][D][H][W] (per_pixel = 1), the two
  *     shapes models/module.py:288,306 accepts.
  */
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TMVS_VERSION 100          /* 0.1.0 */
+#define TMVS_VERSION 200          /* 0.2.0: per-call flags, no process-wide state */
 #define TMVS_MAX_SRC_VIEWS 16     /* source views per launch */
 #define TMVS_MAX_DEPTH 256        /* depth planes per pixel */
 
@@ -49,16 +50,26 @@ enum {
 typedef void *tmvs_stream_t;
 
 /*
- * The reference's own CPU and CUDA executions of models/module.py:311-313 differ in the last bit: ATen's CPU kernel
- * divides by the python scalar (W-1)/2, ATen's CUDA kernel multiplies by its reciprocal.  At 1152x1600 that moves
- * sample positions by ~1e-4 px and cost volumes by ~2e-4 (max-norm).  TMVS_ARITH_IEEE (default) follows the CPU
- * arithmetic -- the one the golden vectors pin --; TMVS_ARITH_ATEN_CUDA follows the CUDA one.  Process-wide setting,
- * read at launch time.
+ * Per-call options (`flags` argument).  The library keeps NO process-wide state and reads NO environment variable:
+ * every choice below travels with the call, so concurrent callers with different options cannot interfere.
+ *
+ * Arithmetic.  The reference's own CPU and CUDA executions of models/module.py:311-313 differ in the last bit: ATen's
+ * CPU kernel divides by the python scalar (W-1)/2, ATen's CUDA kernel multiplies by its reciprocal.  At 1152x1600 that
+ * moves sample positions by ~1e-4 px and cost volumes by ~2e-4 (max-norm).  Without TMVS_F_ARITH_ATEN_CUDA the kernels
+ * follow the CPU arithmetic (what the CPU-generated golden vectors pin); with it they follow the CUDA one -- the
+ * arithmetic of the device the reference would have run on, and the default of the Python drop-in for CUDA tensors.
  */
 #define TMVS_ARITH_IEEE 0
 #define TMVS_ARITH_ATEN_CUDA 1
-int tmvs_set_reference_arithmetic(int mode);
-int tmvs_get_reference_arithmetic(void);
+#define TMVS_F_ARITH_ATEN_CUDA 0x1u   /* follow ATen's CUDA arithmetic (reciprocal multiply) instead of the CPU one */
+#define TMVS_F_RT_DEVICE       0x2u   /* rot_trans is a DEVICE array (same [Nsrc][B][12] layout), read by the kernels in
+                                         place: nothing is copied to the host and nothing synchronises */
+#define TMVS_F_FWD_TMA         0x4u   /* tmvs_costvol_fwd: TMA-staged shared-memory gather (tmvs_costvol_tma.cu) where
+                                         it applies; same results up to fp32 re-association; measured slower */
+#define TMVS_F_BWD_SCAN        0x8u   /* tmvs_costvol_bwd: grad_src through the tile-scan kernels only (no cell tables) */
+#define TMVS_F_PACK_LDG        0x10u  /* tmvs_pack_sources: register-transpose kernel instead of the TMA engine */
+#define TMVS_F_TABLE_MB(mb)    ((unsigned)(mb) << 16)   /* tmvs_costvol_bwd(+_workspace_bytes): cap of the cell-table
+                                         workspace in MiB (0 = default 3072), e.g. to exercise the multi-pass path */
 
 int tmvs_version(void);
 /*
@@ -84,7 +95,7 @@ size_t tmvs_packed_bytes(int n_src, int B, int C, int H, int W);
  * and channels_last tensors are both read in place.   src is a HOST array of device pointers.
  */
 int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
-                      float *packed, int B, int C, int H, int W, tmvs_stream_t stream);
+                      float *packed, int B, int C, int H, int W, unsigned flags, tmvs_stream_t stream);
 
 /*
  * Drop-in homo_warping (models/module.py:284-322) for ONE source view: materialises the
@@ -92,7 +103,18 @@ int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC
  * rot_trans = host [B][12].
  */
 int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const float *depth, int per_pixel,
-                       float *out, int B, int C, int D, int H, int W, tmvs_stream_t stream);
+                       float *out, int B, int C, int D, int H, int W, unsigned flags, tmvs_stream_t stream);
+
+/*
+ * Backward of the drop-in homo_warping wrt the source features (autograd of F.grid_sample, models/module.py:318-320,
+ * for an arbitrary upstream gradient): grad_out [B][C][D][H][W] -> grad_src [B][C][H][W] (contiguous NCHW, overwritten).
+ * Deterministic and free of floating-point atomics: every source pixel gathers its contributions through the
+ * cell table of tmvs_costvol_bwd.  workspace >= tmvs_homo_warp_bwd_workspace_bytes().
+ */
+int tmvs_homo_warp_bwd(const float *rot_trans, const float *depth, int per_pixel, const float *grad_out,
+                       float *grad_src, void *workspace, size_t workspace_bytes, int B, int C, int D, int H, int W,
+                       unsigned flags, tmvs_stream_t stream);
+size_t tmvs_homo_warp_bwd_workspace_bytes(int B, int C, int D, int H, int W);
 
 /*
  * Fused warp + bilinear sampling + correlation (+ view-weighted aggregation):
@@ -108,7 +130,23 @@ int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const f
 int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
                      const float *packed, const float *rot_trans, const float *depth, int per_pixel,
                      const float *view_weights, float *sim_views, float *agg,
-                     int B, int C, int D, int H, int W, int n_src, tmvs_stream_t stream);
+                     int B, int C, int D, int H, int W, int n_src, unsigned flags, tmvs_stream_t stream);
+
+/*
+ * The same kernel fed from per-view packed maps that live anywhere on the device -- what a scan-level cache of
+ * packed feature pyramids hands over (each view of a scan is a source view of several reference views; it is
+ * packed once, datasets/general_eval.py:25-57 pairing) -- and with the view weights read at a coarser stage's
+ * resolution:
+ *   packed_views   HOST array [n_src] of device pointers, each one view's packed map [B][H][Wb][C4][8][4]
+ *   view_weights   [B][Nsrc][vw_h][vw_w]; the kernel reads w[y >> vw_shift][x >> vw_shift], i.e. the nearest x2
+ *                  upsampling of models/TransMVSNet.py:193-194 applied vw_shift times, without materialising it
+ *                  (vw_shift = 0: full resolution, vw_h = H, vw_w = W).
+ */
+int tmvs_costvol_fwd_cached(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                            const float *const *packed_views, const float *rot_trans, const float *depth,
+                            int per_pixel, const float *view_weights, int vw_shift, int vw_h, int vw_w,
+                            float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src,
+                            unsigned flags, tmvs_stream_t stream);
 
 /*
  * Aggregation alone (stage 1 after PixelwiseNet, models/TransMVSNet.py:71-72,88-93):
@@ -193,8 +231,8 @@ int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64
                      const float *packed, const float *rot_trans, const float *depth, int per_pixel,
                      const float *grad_views, float *grad_ref, float *grad_src, void *workspace,
                      size_t workspace_bytes, int B, int C, int D, int H, int W, int n_src,
-                     tmvs_stream_t stream);
-size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src);
+                     unsigned flags, tmvs_stream_t stream);
+size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src, unsigned flags);
 
 /*
  * Read-out (models/TransMVSNet.py:99-103 + models/module.py:474-482) in one pass:

@@ -44,6 +44,16 @@ def save(name, **arrays):
     print(f"{name:28s} {os.path.getsize(path) / 1024:8.1f} KiB")
 
 
+def warp_with_grad(src, src_proj, ref_proj, depth, seed):
+    """The reference's homo_warping and its autograd wrt src_fea (through F.grid_sample, models/module.py:318-320) for a
+    seeded, arbitrary upstream gradient [B,C,D,H,W]."""
+    s = src.clone().requires_grad_(True)
+    out = homo_warping(s, src_proj, ref_proj, depth)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(seed))
+    (gsrc,) = torch.autograd.grad(out, s, gout)
+    return out.detach(), gout, gsrc
+
+
 def projections(pm):
     views = torch.unbind(pm, 1)
     return [compose_projection(v) for v in views]
@@ -55,14 +65,14 @@ def warp_cases():
     projs = projections(st.proj_matrix)
     for tag, depth in (("perpixel", st.depth_values), ("planes", st.depth_values[:, :, 3, 5].contiguous())):
         src = st.features[1]
-        out = homo_warping(src, projs[1], projs[0], depth)
+        out, gout, gsrc = warp_with_grad(src, projs[1], projs[0], depth, 31)
         save(f"warp_{tag}", src=src, src_proj=projs[1], ref_proj=projs[0], depth=depth,
-             rot_trans=relative_rot_trans(projs[1], projs[0]), out=out)
+             rot_trans=relative_rot_trans(projs[1], projs[0]), out=out, grad_out=gout, grad_src=gsrc)
     # (b) identity warp: src_proj == ref_proj  =>  every depth plane reproduces the source
     src = st.features[2]
-    out = homo_warping(src, projs[0], projs[0], st.depth_values)
+    out, gout, gsrc = warp_with_grad(src, projs[0], projs[0], st.depth_values, 32)
     save("warp_identity", src=src, src_proj=projs[0], ref_proj=projs[0], depth=st.depth_values,
-         rot_trans=relative_rot_trans(projs[0], projs[0]), out=out)
+         rot_trans=relative_rot_trans(projs[0], projs[0]), out=out, grad_out=gout, grad_src=gsrc)
     # (c) exact-integer sample coordinates: pure x/y translation, power-of-two depths
     b, c, h, w = 1, 4, 8, 12
     g = torch.Generator().manual_seed(3)
@@ -72,17 +82,17 @@ def warp_cases():
     src_p[0, 0, 3] = 8.0
     src_p[0, 1, 3] = -16.0
     depth = torch.tensor([[1.0, 2.0, 4.0, 8.0, 16.0]])
-    out = homo_warping(src, src_p, ref_p, depth)
+    out, gout, gsrc = warp_with_grad(src, src_p, ref_p, depth, 33)
     save("warp_integer", src=src, src_proj=src_p, ref_proj=ref_p, depth=depth,
-         rot_trans=relative_rot_trans(src_p, ref_p), out=out)
+         rot_trans=relative_rot_trans(src_p, ref_p), out=out, grad_out=gout, grad_src=gsrc)
     # (d) points behind the source camera (z < 1e-6) and huge coordinates (z tiny positive)
     src_p = torch.eye(4)[None].clone()
     src_p[0, 2, 3] = -4.0          # z = depth - 4
     src_p[0, 0, 3] = 1.0
     depth = torch.tensor([[1.0, 3.999999, 4.0, 4.0000005, 4.000001, 4.5, 6.0, 1e-9]])
-    out = homo_warping(src, src_p, ref_p, depth)
+    out, gout, gsrc = warp_with_grad(src, src_p, ref_p, depth, 34)
     save("warp_behind", src=src, src_proj=src_p, ref_proj=ref_p, depth=depth,
-         rot_trans=relative_rot_trans(src_p, ref_p), out=out)
+         rot_trans=relative_rot_trans(src_p, ref_p), out=out, grad_out=gout, grad_src=gsrc)
 
 
 class _Capture(torch.nn.Module):

@@ -24,10 +24,12 @@ def test_stage1_pairwise_errors():
         dev = pipeline.stage_to_device(st, "cuda:0")
         t_cuda = torch_port.cost_volume(dev["features"], st.proj_matrix.cuda(), dev["depth_values"],
                                         dev["view_weights"])[0].squeeze(1).cpu().numpy()
-    ours = pipeline.run_stage(dev)["similarity"].cpu().numpy()
-    ops.set_reference_arithmetic("cuda")
-    ours_cuda = pipeline.run_stage(dev)["similarity"].cpu().numpy()
-    ops.set_reference_arithmetic("cpu")
+    with ops.reference_arithmetic("cpu"):
+        ours = pipeline.run_stage(dev)["similarity"].cpu().numpy()
+    with ops.reference_arithmetic("cuda"):
+        ours_cuda = pipeline.run_stage(dev)["similarity"].cpu().numpy()
+    # the drop-in's default on CUDA tensors is the arithmetic of the device the reference would have run on
+    assert np.array_equal(pipeline.run_stage(dev)["similarity"].cpu().numpy(), ours_cuda)
     pairs = {"ours(cpu arith) vs torch CPU": (ours, t_cpu), "C oracle vs torch CPU": (c_or, t_cpu),
              "ours(cpu arith) vs C oracle": (ours, c_or), "torch CUDA vs torch CPU": (t_cuda, t_cpu),
              "ours(cuda arith) vs torch CUDA": (ours_cuda, t_cuda), "ours(cpu arith) vs torch CUDA": (ours, t_cuda)}

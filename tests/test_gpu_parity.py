@@ -11,11 +11,21 @@ import torch
 from conftest import (COSTVOL_REL, DEPTH_FRAC, DEPTHNET_GIVEN, PROB_ABS, WARP_CASES, assert_costvol_close, golden,
                       rel_err)
 import transmvsnet_b200 as tm
-from transmvsnet_b200 import geometry, ops, pipeline, synthetic
+from transmvsnet_b200 import _lib, geometry, ops, pipeline, synthetic
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _cpu_reference_arithmetic():
+    """The golden vectors and the C oracle were produced by the reference's CPU execution: every test of this file
+    compares against them, so the kernels are asked (per call, include/tmvs.h TMVS_F_ARITH_ATEN_CUDA off) to follow
+    ATen's CPU arithmetic.  The CUDA arithmetic -- the drop-in's default -- is pinned against the reference's stock
+    CUDA execution in test_gpu_vs_stock_cuda.py / test_gpu_dropin_reference.py."""
+    with ops.reference_arithmetic("cpu"):
+        yield
 
 
 def cu(a):
@@ -32,16 +42,15 @@ def test_homo_warping_golden(name):
     assert np.array_equal(out.cpu().numpy() == 0, g["out"] == 0)       # zero padding / z<1e-6 exactly
 
 
-def test_pack_tma_and_register_transpose_paths_agree(monkeypatch):
+def test_pack_tma_and_register_transpose_paths_agree():
     """The layout pre-pass has a TMA-engine kernel (contiguous NCHW, C in {8,16,32,64}, W % 4 == 0) and the
     register-transpose kernels it falls back to: identical packed features wherever a pixel exists (the padding pixels
     of a row's last 8-pixel block are never read)."""
     torch.manual_seed(4)
     for b, c, h, w in ((1, 32, 24, 64), (2, 16, 17, 100), (1, 8, 9, 132), (2, 64, 5, 8), (1, 32, 288, 400)):
         feats = [torch.randn(b, c, h, w, device=DEV) for _ in range(3)]
-        monkeypatch.setenv("TMVS_PACK_PATH", "ldg")
-        ref = ops.pack_sources(feats)
-        monkeypatch.delenv("TMVS_PACK_PATH", raising=False)
+        with ops.extra_flags(_lib.F_PACK_LDG):
+            ref = ops.pack_sources(feats)
         got = ops.pack_sources(feats)                           # [N,B,H,Wb,C4,8,4]
         valid = (torch.arange(ref.shape[3], device=DEV)[:, None] * 8 + torch.arange(8, device=DEV)[None, :]) < w
         m = valid[None, None, None, :, None, :, None].expand_as(ref)
@@ -51,11 +60,19 @@ def test_pack_tma_and_register_transpose_paths_agree(monkeypatch):
         assert torch.equal(nchw, torch.stack(feats, 0))
 
 
-def test_homo_warping_refuses_to_drop_gradients():
-    g = golden(WARP_CASES[0])
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_homo_warping_is_differentiable_like_the_reference(name):
+    """models/module.py:318-320 is differentiable wrt src_fea through F.grid_sample; so is the drop-in, for an
+    ARBITRARY upstream gradient [B,C,D,H,W] (golden: the reference's autograd on the CPU), deterministically."""
+    g = golden(name)
     src = cu(g["src"]).requires_grad_(True)
-    with pytest.raises(RuntimeError, match="forward-only"):
-        tm.homo_warping(src, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"]))
+    out = tm.homo_warping(src, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"]))
+    assert out.requires_grad
+    out.backward(cu(g["grad_out"]))
+    assert_costvol_close(src.grad.cpu().numpy(), g["grad_src"], name + " grad_src")
+    src2 = cu(g["src"]).requires_grad_(True)
+    tm.homo_warping(src2, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"])).backward(cu(g["grad_out"]))
+    assert torch.equal(src.grad, src2.grad)                          # no float atomics: bit-reproducible
     with torch.no_grad():
         assert tm.homo_warping(src, cu(g["src_proj"]), cu(g["ref_proj"]), cu(g["depth"])).requires_grad is False
 
@@ -128,7 +145,7 @@ def test_cost_volume_full_size_stage3_vs_oracle():
     assert_costvol_close(agg.cpu().numpy(), o_agg, "full-size stage 3")
 
 
-def test_tma_and_l1_paths_agree(monkeypatch):
+def test_tma_and_l1_paths_agree():
     """The TMA-staged shared-memory kernel and the L1 global-gather kernel land on the same sample positions and
     weights (same coordinate arithmetic); only the order of the channel sum differs (the L1 kernel accumulates even
     and odd channels separately for FFMA2), so they agree to fp32 re-association: <= 2e-6 of the volume's range.
@@ -145,9 +162,8 @@ def test_tma_and_l1_paths_agree(monkeypatch):
     cases.append((st, rt))
     for st, rt in cases:
         args = (cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(st.depth_values), cu(st.view_weights))
-        monkeypatch.setenv("TMVS_COSTVOL_PATH", "tma")
-        agg_t, views_t = tm.cost_volume(*args, want_views=True)
-        monkeypatch.delenv("TMVS_COSTVOL_PATH", raising=False)
+        with ops.extra_flags(_lib.F_FWD_TMA):
+            agg_t, views_t = tm.cost_volume(*args, want_views=True)
         agg_l, views_l = tm.cost_volume(*args, want_views=True)
         for a, b in ((agg_t, agg_l), (views_t, views_l)):
             assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
@@ -298,9 +314,9 @@ def test_cost_volume_backward_minification_fallback():
     assert torch.equal(gsrc, gsrc2)
 
 
-def test_grad_src_cell_table_and_tile_scan_paths_agree(monkeypatch):
+def test_grad_src_cell_table_and_tile_scan_paths_agree():
     """grad_src has two atomic-free implementations: the global cell table (default) and the tile-scan kernels it
-    falls back to when a cell overflows (TMVS_BWD_SRC_PATH=scan forces them).  Same contributions, different fixed
+    falls back to when a cell overflows (the TMVS_F_BWD_SCAN flag forces them).  Same contributions, different fixed
     summation orders: they agree to fp32 re-association, and each is bit-reproducible.  Cases: cascade shapes with
     per-pixel hypotheses (parity collisions + overflow slots in use), [B,D] hypotheses, a ragged 37x53 map."""
     cases = []
@@ -317,37 +333,33 @@ def test_grad_src_cell_table_and_tile_scan_paths_agree(monkeypatch):
         b, d, h, w = st.depth_values.shape
         gv = cu(torch.randn(len(st.features) - 1, b, d, h, w, generator=torch.Generator().manual_seed(5)))
         run = lambda: ops.costvol_backward_packed(cu(st.features[0]), packed, rt, cu(dv), gv, need_ref=False)[1]
-        monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
         g_cells, g_cells2 = run(), run()
-        monkeypatch.setenv("TMVS_BWD_SRC_PATH", "scan")
-        g_scan = run()
-        monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+        with ops.extra_flags(_lib.F_BWD_SCAN):
+            g_scan = run()
         assert torch.equal(g_cells, g_cells2)
         assert float((g_cells - g_scan).abs().max()) <= 3e-6 * float(g_scan.abs().max())
         o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, dv, gv.cpu())
         assert_costvol_close(g_cells.cpu().numpy(), o_src, f"stage {st.stage} grad_src (cell table)")
 
 
-def test_grad_src_cell_table_multi_group_and_multi_pass(monkeypatch):
+def test_grad_src_cell_table_multi_group_and_multi_pass():
     """Plumbing of the cell-table path: a batch that needs two launch groups (rot/trans travel as kernel parameters,
     64 (view, batch) slots per launch) and a table workspace capped so that the pairs of a group go through the tables
-    in several passes (TMVS_BWD_TABLE_MB) -- same result as the uncapped run, bit for bit, and equal to the oracle."""
+    in several passes (TMVS_F_TABLE_MB) -- same result as the uncapped run, bit for bit, and equal to the oracle."""
     st = synthetic.make_stage(2, batch=23, n_views=4, height=32, width=48, seed=17)       # 3 x 23 = 69 pairs > 64
     rt = geometry.stage_rot_trans(st.proj_matrix)
     n, (b, d, h, w) = 3, st.depth_values.shape
     gv = torch.randn(n, b, d, h, w, generator=torch.Generator().manual_seed(6))
     o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, st.depth_values, gv)
-    monkeypatch.delenv("TMVS_BWD_TABLE_MB", raising=False)
     gref, gsrc = _backward_once(st, rt, cu(gv))
     assert_costvol_close(gref.cpu().numpy(), o_ref, "two launch groups grad_ref")
     assert_costvol_close(gsrc.cpu().numpy(), o_src, "two launch groups grad_src")
-    monkeypatch.setenv("TMVS_BWD_TABLE_MB", "1")                 # ~1.3 MB per pair at this size: one pair per pass
-    _, gsrc_capped = _backward_once(st, rt, cu(gv))
-    monkeypatch.delenv("TMVS_BWD_TABLE_MB", raising=False)
+    with ops.extra_flags(_lib.f_table_mb(1)):                    # ~1.3 MB per pair at this size: one pair per pass
+        _, gsrc_capped = _backward_once(st, rt, cu(gv))
     assert torch.equal(gsrc, gsrc_capped)
 
 
-def test_grad_src_local_overflow_falls_back_per_tile(monkeypatch):
+def test_grad_src_local_overflow_falls_back_per_tile():
     """A steep ramp in the hypotheses of one image region makes dozens of reference pixels land on the same source
     pixel there (more than a cell's 4 + 2 slots): the footprints that find no slot flag only the 32x8 source tiles they
     touch, the tile-scan kernels redo exactly those tiles and the cell tables serve the rest.  Result: equal to the
@@ -371,11 +383,9 @@ def test_grad_src_local_overflow_falls_back_per_tile(monkeypatch):
     o_ref, o_src = oracle.costvol_bwd(st.features[0], torch.stack(st.features[1:], 0), rt, dv, gv)
     packed = ops.pack_sources([cu(f) for f in st.features[1:]])
     run = lambda: ops.costvol_backward_packed(cu(st.features[0]), packed, rt, cu(dv), cu(gv), need_ref=False)[1]
-    monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
     a, b2 = run(), run()
-    monkeypatch.setenv("TMVS_BWD_SRC_PATH", "scan")
-    scan = run()
-    monkeypatch.delenv("TMVS_BWD_SRC_PATH", raising=False)
+    with ops.extra_flags(_lib.F_BWD_SCAN):
+        scan = run()
     assert torch.equal(a, b2)
     assert_costvol_close(a.cpu().numpy(), o_src, "locally minified grad_src")
     assert float((a - scan).abs().max()) <= 3e-6 * float(scan.abs().max())

@@ -1,0 +1,129 @@
+"""Scan-level pipeline and the boundary options added in round 2, on the GPU through the C ABI.
+
+* rot/trans read from DEVICE memory (TMVS_F_RT_DEVICE) == passed by value from the host, bit for bit, forward and
+  backward; DepthNet.forward with the projection matrices on the GPU (as the reference's test.py holds them) runs
+  without a single host synchronisation (torch.cuda.set_sync_debug_mode("error")).
+* view weights read at the stage-1 resolution inside the kernel (vw_shift) == the materialised nearest x2 upsampling of
+  models/TransMVSNet.py:193-194; per-view packed maps (tmvs_costvol_fwd_cached) == the contiguous pack.
+* HostPipeline.process_scan (each view uploaded and packed once per scan) == the per-view cascade on the same inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import transmvsnet_b200 as tm
+from transmvsnet_b200 import geometry, ops, pipeline, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def test_device_rot_trans_equals_host_rot_trans_forward_and_backward():
+    for stage, hw in ((1, (96, 160)), (2, (72, 104)), (3, (40, 72))):
+        st = synthetic.make_stage(stage, batch=3, n_views=4, height=hw[0], width=hw[1], seed=31)
+        rt_host = geometry.stage_rot_trans(st.proj_matrix)
+        assert not rt_host.is_cuda
+        rt_dev = rt_host.to(DEV)
+        feats = [cu(f) for f in st.features]
+        outs = []
+        for rt in (rt_host, rt_dev):
+            fs = [f.detach().requires_grad_(True) for f in feats]
+            agg, views = tm.cost_volume(fs[0], fs[1:], rt, cu(st.depth_values), cu(st.view_weights), want_views=True)
+            (agg.sum() + 0.5 * views.sum()).backward()
+            outs.append([agg.detach(), views.detach()] + [f.grad for f in fs])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        # the 4x4 algebra itself on the device: the matrices the reference would have computed there
+        rt_gpu_algebra = geometry.stage_rot_trans(cu(st.proj_matrix))
+        assert rt_gpu_algebra.is_cuda and tuple(rt_gpu_algebra.shape) == tuple(rt_host.shape)
+        assert float((rt_gpu_algebra.cpu() - rt_host).abs().max()) <= 1e-3 * float(rt_host.abs().max())
+        warp_h = ops.homo_warp_packed(ops.pack_sources(feats[1:2])[0], rt_host[0], cu(st.depth_values), feats[1].shape[1],
+                                      feats[1].shape[3])
+        warp_d = ops.homo_warp_packed(ops.pack_sources(feats[1:2])[0], rt_dev[0], cu(st.depth_values), feats[1].shape[1],
+                                      feats[1].shape[3])
+        assert torch.equal(warp_h, warp_d)
+
+
+def test_depthnet_forward_with_gpu_projections_never_synchronises():
+    """models/TransMVSNet.py:198-215 hands DepthNet the projection matrices on the GPU (test.py: tocuda(sample)).  The
+    round-1 path ended the 4x4 algebra in .cpu() -- three blocking round trips per reference view; now nothing in
+    DepthNet.forward may synchronise (inference with given weights: stages 2/3 of the cascade)."""
+    st = synthetic.make_stage(2, batch=1, n_views=4, height=96, width=128, seed=33)
+    net = tm.DepthNet().to(DEV).eval()
+    feats = [cu(f) for f in st.features]
+    pm, dv, vw = cu(st.proj_matrix), cu(st.depth_values), cu(st.view_weights)
+    ident = torch.nn.Identity()
+    with torch.no_grad():
+        ref = net(feats, pm, dv, st.num_depth, ident, view_weights=vw)          # warm-up: allocations, lazy init
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            out = net(feats, pm, dv, st.num_depth, ident, view_weights=vw)
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.equal(out["depth"], ref["depth"]) and torch.equal(out["prob_volume"], ref["prob_volume"])
+
+
+def test_view_weights_read_at_stage1_resolution_and_per_view_packed_maps():
+    cascade = synthetic.make_cascade(batch=2, n_views=4, height=96, width=160, seed=35)
+    vw1 = cu(cascade[0].view_weights)
+    for s, st in enumerate(cascade):
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        feats = [cu(f) for f in st.features]
+        packed = ops.pack_sources(feats[1:])
+        full, _ = ops.cost_volume_packed(feats[0], packed, rt, cu(st.depth_values), cu(st.view_weights), False, True)
+        shifted, _ = ops.cost_volume_packed(feats[0], packed, rt, cu(st.depth_values), vw1, False, True, vw_shift=s)
+        assert torch.equal(full, shifted), f"stage {s + 1}: in-kernel nearest upsampling"
+        # the same views as separate allocations, in another order of memory
+        singles = [ops.pack_sources([f])[0].clone() for f in reversed(feats[1:])][::-1]
+        cached, views_c = ops.cost_volume_packed(feats[0], singles, rt, cu(st.depth_values), vw1, True, True, vw_shift=s)
+        _, views_p = ops.cost_volume_packed(feats[0], packed, rt, cu(st.depth_values), None, True, False)
+        assert torch.equal(full, cached) and torch.equal(views_c, views_p)
+
+
+def test_packed_maps_of_another_shape_are_refused():
+    st = synthetic.make_stage(2, batch=1, n_views=3, height=64, width=96, seed=36)
+    feats = [cu(f) for f in st.features]
+    rt = geometry.stage_rot_trans(st.proj_matrix)
+    wrong = ops.pack_sources([f[:, :8].contiguous() for f in feats[1:]])             # packed for C = 8, features C = 16
+    with pytest.raises(RuntimeError, match="packed sources"):
+        ops.cost_volume_packed(feats[0], wrong, rt, cu(st.depth_values), cu(st.view_weights), False, True)
+    with pytest.raises(RuntimeError, match="rot_trans"):
+        ops.cost_volume_packed(feats[0], ops.pack_sources(feats[1:]), rt[:1], cu(st.depth_values), cu(st.view_weights),
+                               False, True)
+    with pytest.raises(RuntimeError, match="do not match"):
+        tm.cost_volume(feats[0], [feats[1][:, :, :-1].contiguous()], rt[:1], cu(st.depth_values), cu(st.view_weights)[:, :1])
+    with pytest.raises(RuntimeError, match="not divisible"):
+        ops.depth_hypotheses(cu(st.cur_depth), st.num_depth, st.interval_pixel, (65, 96), 2)
+
+
+def test_process_scan_equals_the_per_view_cascade():
+    """Same inputs through (a) HostPipeline.process_scan -- one upload + one pack per view, cached packed maps, weights
+    read at stage-1 resolution -- and (b) the plain per-view path (pack the four sources, materialised weights):
+    identical maps for every job and stage, twice in a row (the second scan reuses the resident slots)."""
+    scan = synthetic.make_scan(7, n_views=5, height=96, width=128, seed=41, logits_pool=3, lean=False)
+    pinned = pipeline.pin_scan(scan)
+    # shared feature maps are pinned once
+    assert pinned.jobs[0][0].features[1] is pinned.pyramids[scan.pairs[0][1][0]][0]
+    pipe = pipeline.HostPipeline(DEV)
+    for rep in range(2):
+        res = pipe.process_scan(pinned)
+        torch.cuda.synchronize()
+        got = [[{k: v.clone() for k, v in stage.items()} for stage in job] for job in res]
+        for j, job in enumerate(scan.jobs):
+            for s, st in enumerate(job):
+                dev = pipeline.stage_to_device(st, DEV)
+                dev["depth_values"] = ops.depth_hypotheses(cu(st.cur_depth), st.num_depth, st.interval_pixel, st.image_hw,
+                                                           st.image_hw[0] // st.bdhw[2])
+                want = pipeline.run_stage(dev)
+                assert torch.equal(got[j][s]["depth"], want["depth"].cpu()), (rep, j, s)
+                assert torch.equal(got[j][s]["photo_confidence"], want["photo_confidence"].cpu()), (rep, j, s)
+    # every view crossed PCIe once: 7 pyramids + 7 x (logits + seeds + stage-1 weights)
+    pyr = sum(m.numel() * 4 for m in scan.pyramids[0])
+    per_job = sum((st.logits.numel() + st.cur_depth.numel()) * 4 for st in scan.jobs[0]) + scan.jobs[0][0].view_weights.numel() * 4
+    assert pipe.h2d_bytes == 7 * (pyr + per_job)

@@ -79,3 +79,67 @@ def test_depthnet_state_dict_keys_match_reference():
     ref_keys = sorted(k[4:] for k in g if k.startswith("pwn."))
     ours = sorted(k[len("pixel_wise_net."):] for k in tm.DepthNet().state_dict())
     assert ours == ref_keys
+
+
+def test_scan_pairs_every_view_is_a_source_n_minus_1_times():
+    """The synthetic pair.txt has the property of DTU's that the feature cache relies on (datasets/general_eval.py:
+    25-57): V jobs, each view the reference view once and a source view of N-1 others."""
+    pairs = synthetic.scan_pairs(49, 5)
+    assert [r for r, _ in pairs] == list(range(49))
+    use = np.zeros(49, int)
+    for r, srcs in pairs:
+        assert len(srcs) == 4 and r not in srcs and len(set(srcs)) == 4
+        for v in srcs:
+            use[v] += 1
+    assert (use == 4).all()
+    # a scan smaller than N views repeats its first source (general_eval.py:47-49 "fill to nviews")
+    r, srcs = synthetic.scan_pairs(3, 5)[0]
+    assert len(srcs) == 4 and set(srcs) <= {1, 2}
+
+
+def test_scan_jobs_alias_the_view_pyramids():
+    scan = synthetic.make_scan(6, n_views=5, height=32, width=48, seed=1)
+    assert len(scan.jobs) == 6 and scan.voxel_views == 6 * sum(s.voxel_views for s in scan.jobs[0])
+    ref, srcs = scan.pairs[2]
+    for s in range(3):
+        job = scan.jobs[2][s]
+        assert job.features[0] is scan.pyramids[ref][s]
+        assert all(job.features[1 + k] is scan.pyramids[v][s] for k, v in enumerate(srcs))
+        assert job.depth_values is None and job.bdhw[1] == synthetic.STAGES[s][1]      # lean: generated on the device
+    assert scan.jobs[2][0].view_weights is not None and scan.jobs[2][1].view_weights is None
+    assert not torch.equal(scan.pyramids[0][0], scan.pyramids[1][0])
+
+
+def test_reference_arithmetic_is_context_local_not_process_wide():
+    """The arithmetic choice is a per-call flag of the C ABI; the Python default is scoped with contextvars, so a thread
+    that asks for the CPU arithmetic does not change what another thread's calls get."""
+    import threading
+    from transmvsnet_b200 import ops
+    seen = {}
+
+    def worker():
+        seen["other thread"] = ops._flags()
+    with ops.reference_arithmetic("cpu"):
+        t = threading.Thread(target=worker)
+        t.start()
+        t.join()
+        seen["inside"] = ops._flags()
+    seen["after"] = ops._flags()
+    assert seen["inside"] & _lib.F_ARITH_ATEN_CUDA == 0
+    assert seen["other thread"] & _lib.F_ARITH_ATEN_CUDA and seen["after"] & _lib.F_ARITH_ATEN_CUDA     # default: CUDA
+    assert ops._flags("cpu") == 0 and ops._flags("cuda") == _lib.F_ARITH_ATEN_CUDA
+    with pytest.raises(ValueError):
+        ops._flags("fp16")
+
+
+def test_library_reads_no_environment_and_keeps_no_arithmetic_state():
+    """no getenv dispatch, no process-global mode in the library."""
+    import glob
+    import os
+    import subprocess
+    csrc = os.path.join(os.path.dirname(_lib.__file__), "csrc")
+    for path in glob.glob(os.path.join(csrc, "*.cu*")):          # (the statically linked CUDA runtime has its own getenv)
+        text = open(path).read()
+        assert "getenv" not in text and "g_arith" not in text, path
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "tmvs_set_reference_arithmetic" not in syms and "tmvs_costvol_fwd_cached" in syms

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_int, c_int64, c_size_t, c_uint, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # TMVS_LIB_PATH: load another build of the same library (scripts/check_bounds.py uses it for the bounds-checking build)
@@ -20,14 +20,16 @@ SIGNATURES = {
     "tmvs_peer_buffer_create": (c_int, [c_size_t, _P, _P]),
     "tmvs_peer_buffer_open": (c_int, [_P, _P]),
     "tmvs_peer_buffer_release": (c_int, [_P, c_int]),
-    "tmvs_set_reference_arithmetic": (c_int, [c_int]),
-    "tmvs_get_reference_arithmetic": (c_int, []),
     "tmvs_error_string": (ctypes.c_char_p, [c_int]),
     "tmvs_packed_bytes": (c_size_t, [c_int] * 5),
-    "tmvs_pack_sources": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, _P]),
-    "tmvs_homo_warp_fwd": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "tmvs_pack_sources": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_uint, _P]),
+    "tmvs_homo_warp_fwd": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
+    "tmvs_homo_warp_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
+    "tmvs_homo_warp_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "tmvs_costvol_fwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P,
-                                 c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
+    "tmvs_costvol_fwd_cached": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, c_int, c_int, c_int,
+                                        _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
     "tmvs_aggregate_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tmvs_finalize_maps_fwd": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
@@ -38,13 +40,25 @@ SIGNATURES = {
     "tmvs_fusibile_workspace_bytes": (c_size_t, [c_int] * 3),
     "tmvs_fusibile_tex_probe": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
     "tmvs_costvol_bwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P,
-                                 c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "tmvs_costvol_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
+                                 c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
+    "tmvs_costvol_bwd_workspace_bytes": (c_size_t, [c_int] * 6 + [c_uint]),
     "tmvs_softmax_wta_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "tmvs_depth_wta": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "tmvs_depth_regression_fwd": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "tmvs_depth_regression_bwd": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
 }
+
+# per-call option bits (include/tmvs.h): the library keeps no process-wide state and reads no environment variable
+F_ARITH_ATEN_CUDA = 0x1
+F_RT_DEVICE = 0x2
+F_FWD_TMA = 0x4
+F_BWD_SCAN = 0x8
+F_PACK_LDG = 0x10
+
+
+def f_table_mb(mb: int) -> int:
+    return int(mb) << 16
+
 
 _LIB = None
 LAUNCHES = 0          # C-ABI kernel launches issued by this process (bench.py reports it)

@@ -4,21 +4,21 @@
 //
 // Replaces models/TransMVSNet.py:71-93.  One thread owns one reference pixel and DC depth
 // planes; its C reference channels live in registers.  Source features are read from the
-// packed [C4][H][W][4] layout: a tap is C4 128-bit loads, and the 32 lanes of a warp (32
-// x-adjacent reference pixels) hit ~512 contiguous bytes per load, which the L1 serves in 4-5
-// wavefronts.  Neighbouring depth planes land on neighbouring source pixels, so the L1 also
-// supplies the cross-plane reuse.  The channel reduction is an in-register dot product taken
+// packed [H][Wb][C4][8 px][4 ch] layout (tmvs_common.cuh): a tap is C4 128-bit loads at immediate
+// 128-byte offsets from one address, and the 32 lanes of a warp (32 x-adjacent reference pixels)
+// hit ~5 lines per load, which the L1 serves in 4-6 wavefronts.  Neighbouring depth planes land
+// on neighbouring source pixels, so the L1 also supplies the cross-plane reuse.  The channel reduction is an in-register dot product taken
 // BEFORE the bilinear blend ("dot first": 4 dots of C, then 4 scalar weights), which is the
 // same sum as the reference's blend-then-multiply up to fp32 re-association.
-#include <stdlib.h>
-#include <string.h>
+#include <atomic>
 
 #include "tmvs_common.cuh"
 
 // TMA-staged variant (tmvs_costvol_tma.cu); TMVS_E_UNSUPPORTED when it does not apply
 int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *packed,
                          const float *rot_trans, const float *depth, int per_pixel, const float *view_weights,
-                         float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, cudaStream_t st);
+                         float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, unsigned flags,
+                         cudaStream_t st);
 
 namespace {
 
@@ -63,8 +63,9 @@ template <int C4T> struct MinBlocks { static constexpr int value = C4T >= 8 ? TM
 template <int C4T, bool EXACT, bool PER_PIXEL, bool VIEWS, bool AGG, bool RECIP>
 __global__ void __launch_bounds__(kTileX * kTileY, MinBlocks<C4T>::value * (8 / TMVS_TILE_Y))
 costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
-                   const float4 *__restrict__ packed, const float *__restrict__ depth,
-                   const float *__restrict__ vw, float *__restrict__ sim_views, float *__restrict__ agg,
+                   const float *__restrict__ depth,
+                   const float *__restrict__ vw, int vw_shift, int vw_w, int vw_hw, float *__restrict__ sim_views,
+                   float *__restrict__ agg,
                    int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W, int n_src,
                    int n_dchunks, const __grid_constant__ TmvsFwdConst kc, const __grid_constant__ TmvsGeom geom)
 {
@@ -105,16 +106,20 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     const size_t slice = (size_t)H * kc.row;
     const float xf = (float)x, yf = (float)y;
 
+    // view weights at a coarser stage's resolution: nearest x2 upsampling (TransMVSNet.py:193-194) read in place
+    const float *vw_p = AGG ? vw + (size_t)b * n_src * vw_hw + (size_t)(y >> vw_shift) * vw_w + (x >> vw_shift) : nullptr;
+
     for (int i = 0; i < n_src; ++i) {
-        const float *rt = geom.rt[i * b_chunk + bl];
+        float rt[12];
+        tmvs_geom_rt(geom, i, bl, b_chunk, rt);
         const TmvsRay ray = tmvs_ray(rt, xf, yf);
         float tx = rt[9], ty = rt[10], tz = rt[11];
         // opaque to the optimiser: keep them in registers for the depth loop instead of re-deriving them (constant-bank
         // index arithmetic and 64-bit multiplies) once per plane
         asm volatile("" : "+f"(tx), "+f"(ty), "+f"(tz));
         float wi = 0.0f;
-        if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
-        const float4 *img = packed + ((size_t)i * b_total + b) * slice;
+        if (AGG) wi = __ldg(vw_p + (size_t)i * vw_hw);
+        const float4 *img = geom.img[i] + (size_t)b * slice;
         asm volatile("" : "+l"(img));
         float *out_v = VIEWS ? sim_views + (((size_t)i * b_total + b) * D + d0) * HW + pix : nullptr;
         const float *dep_p = dep_base;
@@ -210,8 +215,9 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
 }
 template <int C4T, bool EXACT, bool PER_PIXEL, bool RECIP>
 int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
-                const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float4 *packed,
-                const float *depth, const float *vw, float *sim_views, float *agg, int b_total, int b_first,
+                const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                const float *depth, const float *vw, int vw_shift, int vw_w, int vw_hw, float *sim_views, float *agg,
+                int b_total, int b_first,
                 int b_chunk, int C, int c4, int D, int H, int W, int n_src, int n_dchunks, const TmvsFwdConst &kc,
                 const TmvsGeom &geom)
 {
@@ -226,20 +232,21 @@ int launch_mode(bool views, bool do_agg, dim3 grid, dim3 block, cudaStream_t st,
 #endif
 #define TMVS_SET_CARVEOUT(V, A)                                                                              \
     {   /* a function attribute is per device: set it once for each device this process launches on */       \
-        static bool done[64] = {};                                                                           \
+        /* an idempotent one-time hint, not state that results depend on: racing threads set the same value */ \
+        static std::atomic<bool> done[64];                                                                   \
         int dev_id = 0;                                                                                      \
         cudaGetDevice(&dev_id);                                                                              \
-        if (dev_id < 0 || dev_id >= 64 || !done[dev_id]) {                                                   \
+        if (dev_id < 0 || dev_id >= 64 || !done[dev_id].load(std::memory_order_acquire)) {                   \
             cudaFuncSetAttribute(costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP>,                     \
                                  cudaFuncAttributePreferredSharedMemoryCarveout, TMVS_CARVEOUT(A));          \
-            if (dev_id >= 0 && dev_id < 64) done[dev_id] = true;                                             \
+            if (dev_id >= 0 && dev_id < 64) done[dev_id].store(true, std::memory_order_release);             \
         }                                                                                                    \
     }
 #define TMVS_LAUNCH(V, A)                                                                                    \
     TMVS_SET_CARVEOUT(V, A)                                                                                  \
     costvol_fwd_kernel<C4T, EXACT, PER_PIXEL, V, A, RECIP><<<grid, block, 0, st>>>(                          \
-        ref, rB, rC, rH, rW, packed, depth, vw, sim_views, agg, b_total, b_first, b_chunk, C, c4, D, H,      \
-        W, n_src, n_dchunks, kc, geom)
+        ref, rB, rC, rH, rW, depth, vw, vw_shift, vw_w, vw_hw, sim_views, agg, b_total, b_first, b_chunk,    \
+        C, c4, D, H, W, n_src, n_dchunks, kc, geom)
     if (views && do_agg) { TMVS_LAUNCH(true, true); }
     else if (views) { TMVS_LAUNCH(true, false); }
     else { TMVS_LAUNCH(false, true); }
@@ -420,48 +427,29 @@ extern "C" int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float 
     return tmvs_aggregate_fwd(sim_views, view_weights, agg, B, D, H, W, n_src, stream);
 }
 
-extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
-                                const float *packed, const float *rot_trans, const float *depth, int per_pixel,
-                                const float *view_weights, float *sim_views, float *agg, int B, int C, int D,
-                                int H, int W, int n_src, tmvs_stream_t stream)
+namespace {
+
+int costvol_fwd_impl(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *const *views,
+                     const float *rot_trans, const float *depth, int per_pixel, const float *view_weights,
+                     int vw_shift, int vw_h, int vw_w, float *sim_views, float *agg, int B, int C, int D, int H, int W,
+                     int n_src, unsigned flags, cudaStream_t st)
 {
-    if (!ref || !packed || !rot_trans || !depth) return TMVS_E_NULL;
-    if (!sim_views && !agg) return TMVS_E_NULL;
-    if (agg && !view_weights) return TMVS_E_NULL;
-    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
-    if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
-    if ((size_t)H * (W + 7) * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;   // 32-bit offsets inside one view
-    if (((uintptr_t)packed & 15) != 0) return TMVS_E_ALIGN;
     const int c4 = (C + 3) / 4;
     const int n_dchunks = (D + kDC - 1) / kDC;
-    const int b_per_launch = TMVS_GEOM_SLOTS / n_src;       // rot/trans ride in the parameter bank
-    cudaStream_t st = (cudaStream_t)stream;
-    // Default: the L1-cached global gather below.  TMVS_COSTVOL_PATH=tma selects the TMA-staged shared-memory
-    // variant (tmvs_costvol_tma.cu; same arithmetic, bit-identical results).  It is opt-in because on the
-    // BASELINE workloads it measured slower (profiles/README.md): its windows must be re-derived per
-    // (tile, view, plane span) from per-pixel hypotheses, and the barrier + copy latency that costs is not
-    // hidden at 2-4 CTAs per SM.
-    const char *path = getenv("TMVS_COSTVOL_PATH");
-    if (path && strcmp(path, "tma") == 0) {
-        int rc = tmvs_costvol_fwd_tma(ref, rB, rC, rH, rW, packed, rot_trans, depth, per_pixel, view_weights, sim_views,
-                                      agg, B, C, D, H, W, n_src, st);
-        if (rc != TMVS_E_UNSUPPORTED) return rc;
-    }
+    const int b_per_launch = TMVS_GEOM_SLOTS / n_src;       // host rot/trans ride in the parameter bank
     dim3 block(kTileX, kTileY);
     const TmvsFwdConst kc = tmvs_fwd_const(C, c4, H, W);
-    const bool recip = tmvs_arith_mode() == TMVS_ARITH_ATEN_CUDA;
+    const bool recip = (flags & TMVS_F_ARITH_ATEN_CUDA) != 0;
+    const int vw_hw = vw_h * vw_w;
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
-        geom.arith = tmvs_arith_mode();
-        for (int i = 0; i < n_src; ++i)
-            for (int bl = 0; bl < bc; ++bl)
-                for (int k = 0; k < 12; ++k)
-                    geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
+        tmvs_geom_fill(geom, rot_trans, flags, n_src, B, b0, bc);
+        for (int i = 0; i < TMVS_MAX_SRC_VIEWS; ++i) geom.img[i] = i < n_src ? (const float4 *)views[i] : nullptr;
         dim3 grid(((W + kTileX - 1) / kTileX) * n_dchunks, (H + kTileY - 1) / kTileY, bc);
         int rc;
 #define TMVS_FWD_ARGS c4, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,                   \
-                      (const float4 *)packed, depth, view_weights, sim_views, agg, B, b0, bc, C, c4, D, H, W, n_src,      \
+                      depth, view_weights, vw_shift, vw_w, vw_hw, sim_views, agg, B, b0, bc, C, c4, D, H, W, n_src,       \
                       n_dchunks, kc, geom
         if (per_pixel)
             rc = recip ? launch_c4<true, true>(TMVS_FWD_ARGS) : launch_c4<true, false>(TMVS_FWD_ARGS);
@@ -471,6 +459,69 @@ extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_
         if (rc != TMVS_OK) return rc;
     }
     return TMVS_OK;
+}
+
+int costvol_fwd_check(const float *ref, const void *packed, const float *rot_trans, const float *depth,
+                      const float *view_weights, const float *sim_views, const float *agg, int B, int C, int D, int H,
+                      int W, int n_src)
+{
+    if (!ref || !packed || !rot_trans || !depth) return TMVS_E_NULL;
+    if (!sim_views && !agg) return TMVS_E_NULL;
+    if (agg && !view_weights) return TMVS_E_NULL;
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return TMVS_E_SHAPE;
+    if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
+    if ((size_t)H * (W + 7) * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;   // 32-bit offsets inside one view
+    return TMVS_OK;
+}
+
+}  // namespace
+
+extern "C" int tmvs_costvol_fwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                                const float *packed, const float *rot_trans, const float *depth, int per_pixel,
+                                const float *view_weights, float *sim_views, float *agg, int B, int C, int D,
+                                int H, int W, int n_src, unsigned flags, tmvs_stream_t stream)
+{
+    int rc = costvol_fwd_check(ref, packed, rot_trans, depth, view_weights, sim_views, agg, B, C, D, H, W, n_src);
+    if (rc != TMVS_OK) return rc;
+    if (((uintptr_t)packed & 15) != 0) return TMVS_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    // Default: the L1-cached global gather.  TMVS_F_FWD_TMA selects the TMA-staged shared-memory variant
+    // (tmvs_costvol_tma.cu; same arithmetic, results equal up to fp32 re-association).  It is opt-in because on the
+    // BASELINE workloads it measured slower: its windows must be re-derived per
+    // (tile, view, plane span) from per-pixel hypotheses, and the barrier + copy latency that costs is not
+    // hidden at 2-4 CTAs per SM.
+    if (flags & TMVS_F_FWD_TMA) {
+        rc = tmvs_costvol_fwd_tma(ref, rB, rC, rH, rW, packed, rot_trans, depth, per_pixel, view_weights, sim_views,
+                                  agg, B, C, D, H, W, n_src, flags, st);
+        if (rc != TMVS_E_UNSUPPORTED) return rc;
+    }
+    const size_t view_words = (size_t)B * tmvs_packed_layout((C + 3) / 4, H, W).slice * 4;
+    const float *views[TMVS_MAX_SRC_VIEWS];
+    for (int i = 0; i < n_src; ++i) views[i] = packed + (size_t)i * view_words;
+    return costvol_fwd_impl(ref, rB, rC, rH, rW, views, rot_trans, depth, per_pixel, view_weights, 0, H, W, sim_views,
+                            agg, B, C, D, H, W, n_src, flags, st);
+}
+
+extern "C" int tmvs_costvol_fwd_cached(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW,
+                                       const float *const *packed_views, const float *rot_trans, const float *depth,
+                                       int per_pixel, const float *view_weights, int vw_shift, int vw_h, int vw_w,
+                                       float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src,
+                                       unsigned flags, tmvs_stream_t stream)
+{
+    int rc = costvol_fwd_check(ref, packed_views, rot_trans, depth, view_weights, sim_views, agg, B, C, D, H, W, n_src);
+    if (rc != TMVS_OK) return rc;
+    for (int i = 0; i < n_src; ++i) {
+        if (!packed_views[i]) return TMVS_E_NULL;
+        if (((uintptr_t)packed_views[i] & 15) != 0) return TMVS_E_ALIGN;
+    }
+    if (agg) {
+        if (vw_shift < 0 || vw_shift > 4 || vw_h <= 0 || vw_w <= 0) return TMVS_E_SHAPE;
+        if (((H - 1) >> vw_shift) >= vw_h || ((W - 1) >> vw_shift) >= vw_w) return TMVS_E_SHAPE;   // weights too small
+    } else {
+        vw_shift = 0; vw_h = H; vw_w = W;
+    }
+    return costvol_fwd_impl(ref, rB, rC, rH, rW, packed_views, rot_trans, depth, per_pixel, view_weights, vw_shift,
+                            vw_h, vw_w, sim_views, agg, B, C, D, H, W, n_src, flags, (cudaStream_t)stream);
 }
 
 extern "C" int tmvs_aggregate_fwd(const float *sim_views, const float *view_weights, float *agg, int B, int D,

@@ -20,13 +20,8 @@
 //   Every output element is written exactly once by its owner, in a fixed summation order: no atomics on
 //   data, bit-reproducible run to run.
 // grad_ref is a plain gather (forward-shaped kernel), split over views and reduced in view order.
-#include <stdlib.h>
-#include <string.h>
-
 #include "tmvs_common.cuh"
 
-extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
-                                 float *packed, int B, int C, int H, int W, tmvs_stream_t stream);
 
 // cell-table path of grad_src (tmvs_costvol_bwd_cells.cu)
 size_t tmvs_bwd_cells_bytes_per_pair(int D, int H, int W);
@@ -34,6 +29,10 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
                        char *tables, int pairs_per_pass, int *flags, int *overflow, int *tile_overflow, int b_total,
                        int b_first, int bc,
                        int n_src, int C, int D, int H, int W, const TmvsGeom &geom, cudaStream_t st);
+
+int tmvs_bwd_warp_cells(const float *depth, int per_pixel, const float *gout, float *grad_src, char *tables, int *flags,
+                        int *overflow, int *tile_overflow, int b, int C, int D, int H, int W, const TmvsGeom &geom,
+                        cudaStream_t st);
 
 namespace {
 
@@ -54,7 +53,8 @@ bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ dept
     const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
     const int b = b_first + bl;
     const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
-    const float *rt = geom.rt[i * b_chunk + bl];
+    float rt[12];
+    tmvs_geom_rt(geom, i, bl, b_chunk, rt);
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
@@ -122,7 +122,8 @@ bwd_bbox_kernel(const float *__restrict__ depth, int4 *__restrict__ bbox, int b_
     const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
     const int b = b_first + bl;
     const size_t HW = (size_t)H * W, pix = (size_t)min(y, H - 1) * W + min(x, W - 1);
-    const float *rt = geom.rt[i * b_chunk + bl];
+    float rt[12];
+    tmvs_geom_rt(geom, i, bl, b_chunk, rt);
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const int tile = blockIdx.y * n_tx + blockIdx.x;
@@ -249,7 +250,8 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
     const int i = blockIdx.z / b_chunk, bl = blockIdx.z - i * b_chunk;
     const int b = b_first + bl;
     const size_t HW = (size_t)H * W;
-    const float *rt = geom.rt[i * b_chunk + bl];
+    float rt[12];
+    tmvs_geom_rt(geom, i, bl, b_chunk, rt);
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
@@ -448,7 +450,7 @@ struct BwdWorkspace {
 #define TMVS_BWD_TABLE_BYTES (3ull << 30)      // cap of the cell-table workspace; at least one pair always fits
 #endif
 
-inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
+inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src, unsigned flags)
 {
     const size_t HW = (size_t)H * W;
     const size_t n_tiles = (size_t)((W + kTX - 1) / kTX) * ((H + kTY - 1) / kTY);
@@ -463,9 +465,8 @@ inline BwdWorkspace bwd_layout(int B, int C, int D, int H, int W, int n_src)
     ws.cells = H <= 32767 && W <= 65535;
     const size_t per_pair = tmvs_bwd_cells_bytes_per_pair(D, H, W);
     const int b_group = B < TMVS_GEOM_SLOTS / n_src ? B : TMVS_GEOM_SLOTS / n_src;
-    // TMVS_BWD_TABLE_MB (environment) overrides the cap, e.g. to exercise the multi-pass path on small inputs
-    const char *cap_env = getenv("TMVS_BWD_TABLE_MB");
-    const size_t cap = cap_env ? (size_t)atoll(cap_env) << 20 : (size_t)TMVS_BWD_TABLE_BYTES;
+    // TMVS_F_TABLE_MB(mb) in the call's flags overrides the cap, e.g. to exercise the multi-pass path on small inputs
+    const size_t cap = (flags >> 16) ? (size_t)(flags >> 16) << 20 : (size_t)TMVS_BWD_TABLE_BYTES;
     size_t pairs = cap / per_pair;
     if (pairs < 1) pairs = 1;
     if (pairs > (size_t)n_src * b_group) pairs = (size_t)n_src * b_group;
@@ -512,16 +513,16 @@ int launch_bwd(int c4, bool want_ref, bool want_src, dim3 grid, cudaStream_t st,
 
 }  // namespace
 
-extern "C" size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src)
+extern "C" size_t tmvs_costvol_bwd_workspace_bytes(int B, int C, int D, int H, int W, int n_src, unsigned flags)
 {
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n_src <= 0) return 0;
-    return bwd_layout(B, C, D, H, W, n_src).total;
+    return bwd_layout(B, C, D, H, W, n_src, flags).total;
 }
 
 extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *packed,
                                 const float *rot_trans, const float *depth, int per_pixel, const float *grad_views,
                                 float *grad_ref, float *grad_src, void *workspace, size_t workspace_bytes, int B,
-                                int C, int D, int H, int W, int n_src, tmvs_stream_t stream)
+                                int C, int D, int H, int W, int n_src, unsigned flags, tmvs_stream_t stream)
 {
     if (!ref || !packed || !rot_trans || !depth || !grad_views || !workspace) return TMVS_E_NULL;
     if (!grad_ref && !grad_src) return TMVS_E_NULL;
@@ -529,7 +530,7 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     if (n_src > TMVS_MAX_SRC_VIEWS || D > TMVS_MAX_DEPTH || C > 64) return TMVS_E_SHAPE;
     if ((size_t)H * (W + 7) * ((C + 3) / 4) > 0x7fffffffu) return TMVS_E_SHAPE;
     if (((uintptr_t)packed & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return TMVS_E_ALIGN;
-    const BwdWorkspace ws = bwd_layout(B, C, D, H, W, n_src);
+    const BwdWorkspace ws = bwd_layout(B, C, D, H, W, n_src, flags);
     if (workspace_bytes < ws.total) return TMVS_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     char *wsp = (char *)workspace;
@@ -537,21 +538,20 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     float *partial = (float *)(wsp + ws.partial);
     int4 *bbox = (int4 *)(wsp + ws.bbox);
     int4 *gbox = (int4 *)(wsp + ws.gbox);
-    int *flags = (int *)(wsp + ws.flags);
-    int *overflow = flags + 3 * (size_t)n_src * B;       // one per (view, batch) pair: some tile of it needs the tile scan
+    int *wflags = (int *)(wsp + ws.flags);
+    int *overflow = wflags + 3 * (size_t)n_src * B;       // one per (view, batch) pair: some tile of it needs the tile scan
     int *tile_overflow = overflow + (size_t)n_src * B;   // one per (pair, 32x8 source tile): that tile needs the tile scan
-    // TMVS_BWD_SRC_PATH=scan forces the tile-scan kernels (the robust path the cell tables fall back to)
-    const char *src_path = getenv("TMVS_BWD_SRC_PATH");
-    const bool use_cells = grad_src && ws.cells && !(src_path && strcmp(src_path, "scan") == 0);
+    // TMVS_F_BWD_SCAN forces the tile-scan kernels (the robust path the cell tables fall back to)
+    const bool use_cells = grad_src && ws.cells && !(flags & TMVS_F_BWD_SCAN);
     const int c4 = (C + 3) / 4;
     const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY, n_tiles = n_tx * n_ty;
     const size_t HW = (size_t)H * W;
     if (grad_src) {   // reference features in the packed layout: the scatter's "value" operand
         const float *one[1] = {ref};
-        int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, stream);
+        int rc = tmvs_pack_sources(one, 1, rB, rC, rH, rW, refp, B, C, H, W, flags & TMVS_F_PACK_LDG, stream);
         if (rc != TMVS_OK) return rc;
         if (use_cells) {
-            cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(4 + n_tiles) * n_src * B * sizeof(int), st);
+            cudaError_t e = cudaMemsetAsync(wflags, 0, (size_t)(4 + n_tiles) * n_src * B * sizeof(int), st);
             if (e != cudaSuccess) return (int)e;
         }
     }
@@ -559,17 +559,13 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
-        geom.arith = tmvs_arith_mode();
-        for (int i = 0; i < n_src; ++i)
-            for (int bl = 0; bl < bc; ++bl)
-                for (int k = 0; k < 12; ++k)
-                    geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
+        tmvs_geom_fill(geom, rot_trans, flags, n_src, B, b0, bc);
         dim3 grid(n_tx, n_ty, n_src * bc);
         int rc;
         if (use_cells) {
             // grad_src through the cell tables; the tile-scan kernels below then run only if a cell overflowed
             rc = tmvs_bwd_src_cells((const float4 *)refp, depth, per_pixel, grad_views, grad_src, wsp + ws.tables,
-                                    ws.pairs_per_pass, flags + 3 * (size_t)n_src * b0, overflow + (size_t)n_src * b0,
+                                    ws.pairs_per_pass, wflags + 3 * (size_t)n_src * b0, overflow + (size_t)n_src * b0,
                                     tile_overflow + (size_t)n_src * b0 * n_tiles, B, b0, bc, n_src, C, D,
                                     H, W, geom, st);
             if (rc != TMVS_OK) return rc;
@@ -591,6 +587,98 @@ extern "C" int tmvs_costvol_bwd(const float *ref, int64_t rB, int64_t rC, int64_
         const size_t n = (size_t)B * C * HW;
         bwd_ref_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, grad_ref, n, n_src);
         int rc = tmvs_launch_status();
+        if (rc != TMVS_OK) return rc;
+    }
+    return TMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------- drop-in warp backward
+namespace {
+
+struct WarpBwdWorkspace {
+    size_t ones, bbox, gbox, flags, tables, total;
+};
+
+inline WarpBwdWorkspace warp_bwd_layout(int D, int H, int W)
+{
+    const size_t n_tiles = (size_t)((W + kTX - 1) / kTX) * ((H + kTY - 1) / kTY);
+    const size_t n_groups = (size_t)(((W + kTX - 1) / kTX + kGroup - 1) / kGroup) * (((H + kTY - 1) / kTY + kGroup - 1) / kGroup);
+    WarpBwdWorkspace ws;
+    ws.ones = 0;
+    ws.bbox = align256(tmvs_packed_layout(1, H, W).slice * 16);
+    ws.gbox = ws.bbox + align256(n_tiles * D * 16);
+    ws.flags = ws.gbox + align256(n_groups * 16);
+    ws.tables = ws.flags + align256((4 + n_tiles) * sizeof(int));
+    ws.total = ws.tables + tmvs_bwd_cells_bytes_per_pair(D, H, W);
+    return ws;
+}
+
+__global__ void __launch_bounds__(256) fill_ones_kernel(float4 *p, size_t n)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) p[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+}
+
+}  // namespace
+
+extern "C" size_t tmvs_homo_warp_bwd_workspace_bytes(int B, int C, int D, int H, int W)
+{
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return warp_bwd_layout(D, H, W).total;
+}
+
+extern "C" int tmvs_homo_warp_bwd(const float *rot_trans, const float *depth, int per_pixel, const float *grad_out,
+                                  float *grad_src, void *workspace, size_t workspace_bytes, int B, int C, int D, int H,
+                                  int W, unsigned flags, tmvs_stream_t stream)
+{
+    if (!rot_trans || !depth || !grad_out || !grad_src || !workspace) return TMVS_E_NULL;
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return TMVS_E_SHAPE;
+    if (D > TMVS_MAX_DEPTH || C > 64 || H > 32767 || W > 65535) return TMVS_E_SHAPE;
+    if (((uintptr_t)workspace & 15) != 0) return TMVS_E_ALIGN;
+    const WarpBwdWorkspace ws = warp_bwd_layout(D, H, W);
+    if (workspace_bytes < ws.total) return TMVS_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *wsp = (char *)workspace;
+    float4 *ones = (float4 *)(wsp + ws.ones);
+    int4 *bbox = (int4 *)(wsp + ws.bbox), *gbox = (int4 *)(wsp + ws.gbox);
+    int *wflags = (int *)(wsp + ws.flags);                  // [0..2] level flags, [3] pair overflow, [4..] per-tile overflow
+    const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY, n_tiles = n_tx * n_ty;
+    const int n_gx = (n_tx + kGroup - 1) / kGroup, n_gy = (n_ty + kGroup - 1) / kGroup, n_groups = n_gx * n_gy;
+    const size_t HW = (size_t)H * W;
+    const size_t n_ones = tmvs_packed_layout(1, H, W).slice;
+    fill_ones_kernel<<<(unsigned)((n_ones + 255) / 256), 256, 0, st>>>(ones, n_ones);
+    dim3 block(kTX, kTY), grid(n_tx, n_ty, 1);
+    for (int b = 0; b < B; ++b) {
+        TmvsGeom geom;
+        tmvs_geom_fill(geom, rot_trans, flags, 1, B, b, 1);
+        cudaError_t e = cudaMemsetAsync(wflags, 0, (size_t)(4 + n_tiles) * sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        int *overflow = wflags + 3, *tile_overflow = wflags + 4;
+        const float *gout_b = grad_out + (size_t)b * C * D * HW;
+        float *gsrc_b = grad_src + (size_t)b * C * HW;
+        int rc = tmvs_bwd_warp_cells(depth, per_pixel, gout_b, gsrc_b, wsp + ws.tables, wflags, overflow, tile_overflow, b,
+                                     C, D, H, W, geom, st);
+        if (rc != TMVS_OK) return rc;
+        // Tiles touched by a footprint that found no slot (folded / strongly minified geometry): the tile-scan kernels
+        // redo exactly those, one channel at a time with ref := 1, C := 1 (k * 1 = the tap weight times the gradient).
+        // Every launch below returns at once when nothing overflowed (device-side gates; no host synchronisation).
+        const float *depth_b = per_pixel ? depth + (size_t)b * D * HW : depth + (size_t)b * D;
+        if (per_pixel) bwd_bbox_kernel<true><<<grid, block, 0, st>>>(depth_b, bbox, 0, 1, D, H, W, n_tx, n_tiles, overflow, geom);
+        else bwd_bbox_kernel<false><<<grid, block, 0, st>>>(depth_b, bbox, 0, 1, D, H, W, n_tx, n_tiles, overflow, geom);
+        bwd_gbox_kernel<<<dim3(n_groups, 1), block, 0, st>>>(bbox, gbox, D, n_tx, n_ty, n_gx, n_tiles, n_groups, overflow);
+        for (int c = 0; c < C; ++c) {
+            const float *g_c = gout_b + (size_t)c * D * HW;
+            float *o_c = gsrc_b + (size_t)c * HW;
+            if (per_pixel)
+                bwd_src_kernel<4, false, true><<<grid, block, 0, st>>>(ones, depth_b, g_c, bbox, gbox, o_c, 1, 0, 1, 1, 1, D, H,
+                                                                       W, n_tx, n_ty, n_tiles, n_gx, n_groups,
+                                                                       tile_overflow, geom);
+            else
+                bwd_src_kernel<4, false, false><<<grid, block, 0, st>>>(ones, depth_b, g_c, bbox, gbox, o_c, 1, 0, 1, 1, 1, D, H,
+                                                                        W, n_tx, n_ty, n_tiles, n_gx, n_groups,
+                                                                        tile_overflow, geom);
+        }
+        rc = tmvs_launch_status();
         if (rc != TMVS_OK) return rc;
     }
     return TMVS_OK;

@@ -27,8 +27,6 @@
 // every (tile, plane) once per source tile its box overlaps, 4-6x, between block-wide barriers).
 #include "tmvs_common.cuh"
 
-int tmvs_arith_mode();
-
 namespace {
 
 constexpr int kTX = 32, kTY = 8;
@@ -71,7 +69,8 @@ cells_register_kernel(const float *__restrict__ depth, CellTables tb, int z0, in
     const int bl = z % b_chunk, b = b_first + bl;
     const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
     const size_t ncell = (size_t)(H + 1) * (W + 1);
-    const float *rt = geom.rt[z];
+    float rt[12];
+    tmvs_geom_rt(geom, z / b_chunk, bl, b_chunk, rt);
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const unsigned id = ((unsigned)y << 16) | (unsigned)x;
@@ -344,6 +343,81 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
     }
 }
 
+// The same gather for the drop-in homo_warping's backward (autograd of F.grid_sample wrt the source features,
+// models/module.py:318-320, for an ARBITRARY upstream gradient): the value scattered by (p, d) is the C-vector
+// grad_out[b, :, d, p] instead of the rank-1  G[d, p] * ref[:, p]  of the fused cost volume, so the owner of source
+// pixel q accumulates  w_tap * grad_out[b, c, d, p]  for every channel, in the same (plane, rank, class) order.
+template <int CT>
+__global__ void __launch_bounds__(kTX * kTY)
+cells_gather_warp_kernel(const float *__restrict__ gout, CellTables tb, float *__restrict__ grad_src, int C, int D, int H,
+                         int W)
+{
+    if (tb.tile_overflow[blockIdx.y * tb.n_tx + blockIdx.x] != 0) return;      // redone by the tile-scan fallback
+    const int qx = blockIdx.x * kTX + threadIdx.x, qy = blockIdx.y * kTY + threadIdx.y;
+    if (qx >= W || qy >= H) return;
+    const unsigned HW = (unsigned)H * (unsigned)W;
+    const unsigned ncell = (unsigned)(H + 1) * (unsigned)(W + 1);
+    const bool has_ovf = tb.flags[0] != 0;
+    const uint4 *par_d = tb.par;
+    const uint2 *ovf_d = tb.ovf;
+    const float2 *pos_d = tb.pos;
+    const float *g_d = gout;                                  // [C][D][HW] of this batch item
+    const size_t c_stride = (size_t)D * HW;
+    const float qxf = (float)qx, qyf = (float)qy;
+    const unsigned c0 = (unsigned)((qy + 1) * (W + 1) + qx + 1);
+    const unsigned wp1 = (unsigned)(W + 1);
+    float acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c] = 0.0f;
+    for (int d = 0; d < D; ++d, par_d += ncell, ovf_d += ncell, pos_d += HW, g_d += HW) {
+        unsigned ids[4][6];
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+            const unsigned cell = c0 - ((cls & 1) ? 1u : 0u) - ((cls & 2) ? wp1 : 0u);
+            const uint4 pr = __ldg(par_d + cell);
+            unsigned *v = ids[cls];
+            v[0] = pr.x; v[1] = pr.y; v[2] = pr.z; v[3] = pr.w; v[4] = kEmptyId; v[5] = kEmptyId;
+            if (has_ovf) {
+                const uint2 ov = __ldg(ovf_d + cell);
+                v[4] = ov.x; v[5] = ov.y;
+            }
+            if (has_ovf) {
+                cswap_u(v[0], v[5]); cswap_u(v[1], v[3]); cswap_u(v[2], v[4]);
+                cswap_u(v[1], v[2]); cswap_u(v[3], v[4]);
+                cswap_u(v[0], v[3]); cswap_u(v[2], v[5]);
+                cswap_u(v[0], v[1]); cswap_u(v[2], v[3]); cswap_u(v[4], v[5]);
+                cswap_u(v[1], v[2]); cswap_u(v[3], v[4]);
+            } else {
+                cswap_u(v[0], v[1]); cswap_u(v[2], v[3]); cswap_u(v[0], v[2]); cswap_u(v[1], v[3]); cswap_u(v[1], v[2]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            if (u >= 4 && !has_ovf) break;
+            if ((ids[0][u] & ids[1][u] & ids[2][u] & ids[3][u]) == kEmptyId) break;
+#pragma unroll
+            for (int cls = 0; cls < 4; ++cls) {
+                const unsigned id = ids[cls][u];
+                if (id == kEmptyId) continue;
+                const unsigned px = id & 0xffffu, py = id >> 16;
+                const unsigned pix = py * (unsigned)W + px;
+                const float2 c = __ldg(pos_d + pix);
+                const float wx = (cls & 1) ? __fsub_rn(c.x, qxf - 1.0f) : __fsub_rn(qxf + 1.0f, c.x);
+                const float wy = (cls & 2) ? __fsub_rn(c.y, qyf - 1.0f) : __fsub_rn(qyf + 1.0f, c.y);
+                const float k = __fmul_rn(wx, wy);
+                const float *gp = g_d + pix;
+#pragma unroll
+                for (int ch = 0; ch < CT; ++ch)
+                    if (ch < C) acc[ch] = fmaf(k, __ldg(gp + (size_t)ch * c_stride), acc[ch]);
+            }
+        }
+    }
+    float *o = grad_src + (size_t)qy * W + qx;
+#pragma unroll
+    for (int ch = 0; ch < CT; ++ch)
+        if (ch < C) o[(size_t)ch * HW] = acc[ch];
+}
+
 inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -417,4 +491,48 @@ int tmvs_bwd_src_cells(const float4 *refp, const float *depth, int per_pixel, co
         if (rc != TMVS_OK) return rc;
     }
     return TMVS_OK;
+}
+
+// grad_src of the drop-in warp for ONE batch item (geom.rt slot 0): registration + fix-up as above with a single pair,
+// then the all-channel gather.  gout = grad_out[b] ([C][D][HW]), grad_src = out[b] ([C][HW]).  flags (3 ints),
+// overflow (1 int) and tile_overflow (n_tiles ints) are zeroed by the caller; flagged tiles are left to its fallback.
+int tmvs_bwd_warp_cells(const float *depth, int per_pixel, const float *gout, float *grad_src, char *tables, int *flags,
+                        int *overflow, int *tile_overflow, int b, int C, int D, int H, int W, const TmvsGeom &geom,
+                        cudaStream_t st)
+{
+    const int n_tx = (W + kTX - 1) / kTX, n_ty = (H + kTY - 1) / kTY;
+    const int n_dchunks = (D + kRegDC - 1) / kRegDC;
+    const size_t ncell = (size_t)(H + 1) * (W + 1), HW = (size_t)H * W;
+    const size_t cell_bytes = align256((size_t)D * ncell * (sizeof(uint4) + sizeof(uint2)));
+    const size_t pos_bytes = align256((size_t)D * HW * sizeof(float2));
+    const size_t n_ctas = (size_t)n_tx * n_ty * n_dchunks;
+    CellTables tb;
+    tb.par = reinterpret_cast<uint4 *>(tables);
+    tb.ovf = reinterpret_cast<uint2 *>(tables + (size_t)D * ncell * sizeof(uint4));
+    tb.pos = reinterpret_cast<float2 *>(tables + cell_bytes);
+    tb.list = reinterpret_cast<uint2 *>(tables + cell_bytes + pos_bytes);
+    tb.list_count = reinterpret_cast<int *>(tables + cell_bytes + pos_bytes + align256(n_ctas * kListCap * sizeof(uint2)));
+    tb.flags = flags;
+    tb.overflow = overflow;
+    tb.tile_overflow = tile_overflow;
+    tb.n_tx = n_tx;
+    tb.n_tiles = n_tx * n_ty;
+    cudaError_t e = cudaMemsetAsync(tables, 0xff, (size_t)D * ncell * (sizeof(uint4) + sizeof(uint2)), st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 block(kTX, kTY), grid_pd(n_tx, n_ty, n_dchunks);
+    // one pair: z0 = 0, b_chunk = 1 -> the kernels' (view, batch) slot is 0 and their batch item is b_first = b
+    if (per_pixel)
+        cells_register_kernel<true><<<grid_pd, block, 0, st>>>(depth, tb, 0, b, 1, D, H, W, n_dchunks, geom);
+    else
+        cells_register_kernel<false><<<grid_pd, block, 0, st>>>(depth, tb, 0, b, 1, D, H, W, n_dchunks, geom);
+    cells_fixup_kernel<1><<<grid_pd, block, 0, st>>>(tb, 0, D, H, W, n_dchunks);
+    cells_fixup_list_kernel<<<(unsigned)n_ctas, 128, 0, st>>>(tb, D, H, W);
+    cells_fixup_kernel<2><<<grid_pd, block, 0, st>>>(tb, 0, D, H, W, n_dchunks);
+    cells_fixup_kernel<3><<<grid_pd, block, 0, st>>>(tb, 0, D, H, W, n_dchunks);
+    dim3 grid_q(n_tx, n_ty, 1);
+    if (C <= 8) cells_gather_warp_kernel<8><<<grid_q, block, 0, st>>>(gout, tb, grad_src, C, D, H, W);
+    else if (C <= 16) cells_gather_warp_kernel<16><<<grid_q, block, 0, st>>>(gout, tb, grad_src, C, D, H, W);
+    else if (C <= 32) cells_gather_warp_kernel<32><<<grid_q, block, 0, st>>>(gout, tb, grad_src, C, D, H, W);
+    else cells_gather_warp_kernel<64><<<grid_q, block, 0, st>>>(gout, tb, grad_src, C, D, H, W);
+    return tmvs_launch_status();
 }

@@ -135,7 +135,8 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     __syncthreads();                                   // mbarrier initialised
 
     for (int i = 0; i < n_src; ++i) {
-        const float *rt = geom.rt[i * b_chunk + bl];
+        float rt[12];
+        tmvs_geom_rt(geom, i, bl, b_chunk, rt);
         const TmvsRay ray = tmvs_ray(rt, xf, yf);
         float wi = 0.0f;
         if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
@@ -348,7 +349,8 @@ int launch_tma(bool views, bool do_agg, dim3 grid, cudaStream_t st, const float 
 // (C/4 not in {2,4,8}, or the driver entry point is unavailable) so the caller uses the L1 kernel.
 int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *packed,
                          const float *rot_trans, const float *depth, int per_pixel, const float *view_weights,
-                         float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, cudaStream_t st)
+                         float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, unsigned flags,
+                         cudaStream_t st)
 {
     if ((C & 3) != 0) return TMVS_E_UNSUPPORTED;
     const int c4 = C / 4;
@@ -375,11 +377,7 @@ int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, i
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
-        geom.arith = tmvs_arith_mode();
-        for (int i = 0; i < n_src; ++i)
-            for (int bl = 0; bl < bc; ++bl)
-                for (int k = 0; k < 12; ++k)
-                    geom.rt[i * bc + bl][k] = rot_trans[((size_t)i * B + b0 + bl) * 12 + k];
+        tmvs_geom_fill(geom, rot_trans, flags, n_src, B, b0, bc);
         dim3 grid(((W + kTileX - 1) / kTileX) * n_dchunks, (H + kTileY - 1) / kTileY, bc);
         int rc;
 #define TMVS_TMA_C4(C4T)                                                                                              \

@@ -2,14 +2,11 @@
 //
 // tmvs_pack_sources: source feature maps (NCHW as produced by the reference's FeatureNet/FMT,
 // models/module.py:399-422, or any strided view such as channels_last) -> the kernel-native
-// blocked channel-last layout [Nsrc][B][C4][H][W][4].  Reads are coalesced along x per channel
+// blocked channel-last layout [Nsrc][B][H][Wb][C4][8 px][4 ch].  Reads are coalesced along x per channel
 // plane, writes are 128-bit and contiguous.
 //
 // tmvs_homo_warp_fwd: models/module.py:284-322 for one view, materialising [B][C][D][H][W]
 // (the reference's own interface; the fused kernels in tmvs_costvol.cu never form this volume).
-#include <stdlib.h>
-#include <string.h>
-
 #include "tmvs_common.cuh"
 
 // TMA-engine variant (tmvs_pack_tma.cu); TMVS_E_UNSUPPORTED when it does not apply
@@ -122,7 +119,8 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
     const int b = b_first + bl;
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)y * W + x;
-    const float *rt = geom.rt[bl];
+    float rt[12];
+    tmvs_geom_rt(geom, 0, bl, b_chunk, rt);
     const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
@@ -176,7 +174,7 @@ extern "C" size_t tmvs_packed_bytes(int n_src, int B, int C, int H, int W)
 }
 
 extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
-                                 float *packed, int B, int C, int H, int W, tmvs_stream_t stream)
+                                 float *packed, int B, int C, int H, int W, unsigned flags, tmvs_stream_t stream)
 {
     if (!src || !packed) return TMVS_E_NULL;
     if (n_src <= 0 || n_src > TMVS_MAX_SRC_VIEWS || B <= 0 || C <= 0 || H <= 0 || W <= 0) return TMVS_E_SHAPE;
@@ -193,9 +191,8 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
     bool aligned = true;
     for (int i = 0; i < n_src; ++i) aligned = aligned && (((uintptr_t)src[i] & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    // contiguous NCHW maps go through the TMA engine (TMVS_PACK_PATH=ldg keeps the register-transpose kernel)
-    const char *pack_path = getenv("TMVS_PACK_PATH");
-    if (!(pack_path && strcmp(pack_path, "ldg") == 0)) {
+    // contiguous NCHW maps go through the TMA engine (TMVS_F_PACK_LDG keeps the register-transpose kernel)
+    if (!(flags & TMVS_F_PACK_LDG)) {
         const int rc = tmvs_pack_sources_tma(src, n_src, sB, sC, sH, sW, packed, B, C, H, W, st);
         if (rc != TMVS_E_UNSUPPORTED) return rc;
     }
@@ -215,7 +212,7 @@ extern "C" int tmvs_pack_sources(const float *const *src, int n_src, int64_t sB,
 }
 
 extern "C" int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_trans, const float *depth, int per_pixel,
-                                  float *out, int B, int C, int D, int H, int W, tmvs_stream_t stream)
+                                  float *out, int B, int C, int D, int H, int W, unsigned flags, tmvs_stream_t stream)
 {
     if (!packed_view || !rot_trans || !depth || !out) return TMVS_E_NULL;
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return TMVS_E_SHAPE;
@@ -228,9 +225,7 @@ extern "C" int tmvs_homo_warp_fwd(const float *packed_view, const float *rot_tra
     for (int b0 = 0; b0 < B; b0 += b_per_launch) {
         const int bc = (B - b0 < b_per_launch) ? B - b0 : b_per_launch;
         TmvsGeom geom;
-        geom.arith = tmvs_arith_mode();
-        for (int bl = 0; bl < bc; ++bl)
-            for (int k = 0; k < 12; ++k) geom.rt[bl][k] = rot_trans[(size_t)(b0 + bl) * 12 + k];
+        tmvs_geom_fill(geom, rot_trans, flags, 1, B, b0, bc);
         dim3 grid((W + 31) / 32, (H + 7) / 8, bc * n_dchunks);
         if (per_pixel)
             homo_warp_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(

@@ -359,7 +359,7 @@ depth_hypotheses_kernel(const float *__restrict__ prev, int prev_planes, int hp,
         // 2-D branch of get_depth_samples (module.py:616-623): the global range cut into D planes
         const float lo = __ldg(prev + (size_t)b * prev_planes), hi = __ldg(prev + (size_t)b * prev_planes + prev_planes - 1);
         const float step = (hi - lo) / (float)(D - 1);
-        for (int d = 0; d < D; ++d) o[(size_t)d * hw] = lo + (float)d * step;
+        for (int d = 0; d < D; ++d) o[(size_t)d * hw] = __fadd_rn(lo, __fmul_rn((float)d, step));   // module.py:618-621: product and sum rounded separately
         return;
     }
     // 3-D branch (module.py:624-632) at the image pixels the trilinear resample (TransMVSNet.py:202-204,
@@ -383,11 +383,13 @@ depth_hypotheses_kernel(const float *__restrict__ prev, int prev_planes, int hp,
         const float fd = (float)d;
         float v;
         if (n == 1) {
-            v = lo[0][0] + fd * st[0][0];
+            v = __fadd_rn(lo[0][0], __fmul_rn(fd, st[0][0]));     // module.py:630-632: no contraction into an FMA
         } else {
-            const float r0 = 0.5f * (lo[0][0] + fd * st[0][0]) + 0.5f * (lo[0][1] + fd * st[0][1]);
-            const float r1 = 0.5f * (lo[1][0] + fd * st[1][0]) + 0.5f * (lo[1][1] + fd * st[1][1]);
-            v = 0.5f * r0 + 0.5f * r1;
+            const float s00 = __fadd_rn(lo[0][0], __fmul_rn(fd, st[0][0])), s01 = __fadd_rn(lo[0][1], __fmul_rn(fd, st[0][1]));
+            const float s10 = __fadd_rn(lo[1][0], __fmul_rn(fd, st[1][0])), s11 = __fadd_rn(lo[1][1], __fmul_rn(fd, st[1][1]));
+            const float r0 = __fadd_rn(__fmul_rn(0.5f, s00), __fmul_rn(0.5f, s01));
+            const float r1 = __fadd_rn(__fmul_rn(0.5f, s10), __fmul_rn(0.5f, s11));
+            v = __fadd_rn(__fmul_rn(0.5f, r0), __fmul_rn(0.5f, r1));
         }
         __stcs(o + (size_t)d * hw, v);
     }
@@ -564,18 +566,6 @@ extern "C" int tmvs_depth_hypotheses_fwd(const float *prev_depth, int prev_plane
     return tmvs_launch_status();
 }
 
-static int g_arith_mode = TMVS_ARITH_IEEE;
-int tmvs_arith_mode() { return g_arith_mode; }
-
-extern "C" int tmvs_set_reference_arithmetic(int mode)
-{
-    if (mode != TMVS_ARITH_IEEE && mode != TMVS_ARITH_ATEN_CUDA) return TMVS_E_UNSUPPORTED;
-    g_arith_mode = mode;
-    return TMVS_OK;
-}
-
-extern "C" int tmvs_get_reference_arithmetic(void) { return g_arith_mode; }
-
 extern "C" int tmvs_version(void) { return TMVS_VERSION; }
 
 // ---- peer-mapped gather buffer (sharding.PeerMapSink) -----------------------------------------------------------------
@@ -592,6 +582,8 @@ extern "C" int tmvs_peer_buffer_create(size_t bytes, void **ptr, unsigned char *
     cudaError_t e = cudaMalloc(ptr, bytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemset(*ptr, 0, bytes);
+    // the fill must have landed before a peer can be handed the buffer: a memset is not ordered against other GPUs' stores
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
     if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return (int)e; }

@@ -10,7 +10,10 @@ PyTorch owns every buffer; the library only launches kernels on the current stre
 """
 from __future__ import annotations
 
+import contextlib
+import contextvars
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -18,12 +21,46 @@ import torch
 from . import _lib
 from .geometry import relative_rot_trans
 
+# Which of the reference's two fp32 arithmetics the kernels follow is a PER-CALL flag of the C ABI (include/tmvs.h).
+# The ops below run on CUDA tensors, so their default is the arithmetic of the device the reference would have run on:
+# ATen's CUDA kernels ("cuda": `x / ((W-1)/2)` as a reciprocal multiply).  "cpu" follows ATen's CPU kernels (true
+# division) -- what the CPU-generated golden vectors and the C oracle pin.  Every op takes `arith=`; a caller that
+# cannot pass it (code under test behind the reference's signatures) scopes it with `reference_arithmetic(...)`,
+# which is context-local (contextvars), not process-wide.  TMVS_ARITH in the environment only seeds that default for
+# test runs; the library itself reads no environment variable.
+_ARITH = contextvars.ContextVar("tmvs_arith", default=os.environ.get("TMVS_ARITH", "cuda"))
+_ARITH_FLAG = {"cpu": 0, "ieee": 0, "cuda": _lib.F_ARITH_ATEN_CUDA}
+# experiment switches of the same kind (scripts/, tests): extra flag bits OR-ed into every call made in the context
+_EXTRA_FLAGS = contextvars.ContextVar("tmvs_extra_flags", default=0)
 
-def set_reference_arithmetic(which: str) -> None:
-    """"cpu" (default): follow ATen's CPU arithmetic (IEEE division by (W-1)/2), the one the golden vectors pin;
-    "cuda": follow ATen's CUDA arithmetic (multiply by the reciprocal) -- see include/tmvs.h."""
-    mode = {"cpu": 0, "ieee": 0, "cuda": 1}[which]
-    _lib.check(_lib.load().tmvs_set_reference_arithmetic(mode), "tmvs_set_reference_arithmetic")
+
+@contextlib.contextmanager
+def reference_arithmetic(which: str):
+    """with reference_arithmetic("cpu"): ...   -- calls made inside follow ATen's CPU arithmetic by default."""
+    if which not in _ARITH_FLAG:
+        raise ValueError(f"arith must be one of {sorted(_ARITH_FLAG)}, got {which!r}")
+    tok = _ARITH.set(which)
+    try:
+        yield
+    finally:
+        _ARITH.reset(tok)
+
+
+@contextlib.contextmanager
+def extra_flags(bits: int):
+    """with extra_flags(_lib.F_FWD_TMA): ...   -- OR `bits` into the flags of every call made inside."""
+    tok = _EXTRA_FLAGS.set(_EXTRA_FLAGS.get() | int(bits))
+    try:
+        yield
+    finally:
+        _EXTRA_FLAGS.reset(tok)
+
+
+def _flags(arith: Optional[str] = None, extra: int = 0) -> int:
+    which = _ARITH.get() if arith is None else arith
+    if which not in _ARITH_FLAG:
+        raise ValueError(f"arith must be one of {sorted(_ARITH_FLAG)}, got {which!r}")
+    return _ARITH_FLAG[which] | _EXTRA_FLAGS.get() | extra
 
 
 def _stream() -> ctypes.c_void_p:
@@ -49,10 +86,28 @@ def _need_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
-def _host_rt(rot_trans) -> torch.Tensor:
-    """rot/trans as a contiguous fp32 CPU tensor (it is passed to the kernels by value)."""
-    rt = torch.as_tensor(rot_trans).detach().to("cpu", torch.float32).contiguous()
-    return rt
+def _rt_arg(rot_trans, shape: Tuple[int, ...], dev: torch.device) -> Tuple[torch.Tensor, int]:
+    """rot/trans for the C ABI: (contiguous fp32 tensor, flag bits).  A host tensor is passed to the kernels by value;
+    a tensor already on the device is read by them in place (TMVS_F_RT_DEVICE) -- no copy, no synchronisation."""
+    rt = torch.as_tensor(rot_trans).detach()
+    if tuple(rt.shape) != tuple(shape):
+        raise _lib.TmvsError(f"rot_trans must be {list(shape)}, got {list(rt.shape)}")
+    rt = rt.to(torch.float32).contiguous()
+    if rt.is_cuda:
+        if rt.device != dev:
+            raise _lib.TmvsError("rot_trans lives on another device than the features")
+        return rt, _lib.F_RT_DEVICE
+    return rt, 0
+
+
+def _check_packed(packed: torch.Tensor, n: Optional[int], b: int, c: int, h: int, w: int) -> None:
+    """A packed map built for other (B, C, H, W) would be indexed with the wrong strides: refuse it."""
+    want = (b, h, (w + 7) // 8, (c + 3) // 4, 8, 4)
+    if n is not None:
+        want = (n,) + want
+    if tuple(packed.shape) != want or not packed.is_contiguous():
+        raise _lib.TmvsError(f"packed sources must be a contiguous {list(want)} tensor (pack_sources of maps shaped like "
+                             f"the reference features [{b},{c},{h},{w}]), got {list(packed.shape)}")
 
 
 def _feature_strides(feats: Sequence[torch.Tensor]) -> Tuple[int, int, int, int]:
@@ -63,18 +118,24 @@ def _feature_strides(feats: Sequence[torch.Tensor]) -> Tuple[int, int, int, int]
     return st
 
 
-def pack_sources(src_feas: Sequence[torch.Tensor]) -> torch.Tensor:
-    """N x [B,C,H,W] (any common strides) -> packed [N,B,H,Wb,C4,8,4] (kernel-native blocked channel-last)."""
+def pack_sources(src_feas: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """N x [B,C,H,W] (any common strides) -> packed [N,B,H,Wb,C4,8,4] (kernel-native blocked channel-last).
+    out: an existing buffer of that shape to pack into (e.g. a slot of a scan-level cache)."""
     lib = _lib.load()
     dev = _need_cuda(*src_feas)
     b, c, h, w = src_feas[0].shape
     n = len(src_feas)
     sb, sc, sh, sw = _feature_strides(src_feas)
-    packed = torch.empty((n, b, h, (w + 7) // 8, (c + 3) // 4, 8, 4), dtype=torch.float32, device=dev)
+    shape = (n, b, h, (w + 7) // 8, (c + 3) // 4, 8, 4)
+    if out is not None:
+        _need_cuda(out)
+        if tuple(out.shape) != shape or not out.is_contiguous():
+            raise _lib.TmvsError(f"pack_sources: out must be a contiguous {list(shape)} tensor, got {list(out.shape)}")
+    packed = out if out is not None else torch.empty(shape, dtype=torch.float32, device=dev)
     ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in src_feas])
     with torch.cuda.device(dev):
         rc = lib.tmvs_pack_sources(ctypes.cast(ptrs, ctypes.c_void_p), n, sb, sc, sh, sw, _ptr(packed),
-                                   b, c, h, w, _stream())
+                                   b, c, h, w, _flags("cpu") & _lib.F_PACK_LDG, _stream())
     _lib.check(rc, "tmvs_pack_sources")
     return packed
 
@@ -88,68 +149,137 @@ def _depth_mode(depth_values: torch.Tensor, b: int, h: int, w: int) -> int:
 
 
 def homo_warp_packed(packed_view: torch.Tensor, rot_trans, depth_values: torch.Tensor, channels: int,
-                     width: int) -> torch.Tensor:
+                     width: int, arith: Optional[str] = None) -> torch.Tensor:
     """packed_view: one view's slice [B,H,Wb,C4,8,4] of pack_sources(); width = the unpadded W."""
     lib = _lib.load()
     dev = _need_cuda(packed_view, depth_values)
     b, h, w = packed_view.shape[0], packed_view.shape[1], width
+    _check_packed(packed_view, None, b, channels, h, w)
     d = depth_values.shape[1]
+    if depth_values.shape[0] != b:
+        raise _lib.TmvsError(f"depth_values has batch {depth_values.shape[0]}, the features {b}")
     mode = _depth_mode(depth_values, b, h, w)
     depth_values = depth_values.contiguous()
-    rt = _host_rt(rot_trans)
+    rt, rt_flag = _rt_arg(rot_trans, (b, 12), dev)
     out = torch.empty((b, channels, d, h, w), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.tmvs_homo_warp_fwd(_ptr(packed_view), ctypes.c_void_p(rt.data_ptr()), _ptr(depth_values), mode,
-                                    _ptr(out), b, channels, d, h, w, _stream())
+                                    _ptr(out), b, channels, d, h, w, _flags(arith, rt_flag), _stream())
     _lib.check(rc, "tmvs_homo_warp_fwd")
     return out
 
 
+class _HomoWarp(torch.autograd.Function):
+    """Drop-in warp with the gradient of F.grid_sample wrt the source features (module.py:318-320); the grid is built
+    under no_grad in the reference (:294-316), so cameras and depth hypotheses get no gradient there either."""
+
+    @staticmethod
+    def forward(ctx, src_fea, rt, depth_values, arith):
+        packed = pack_sources([src_fea.detach()])
+        ctx.save_for_backward(rt, depth_values)
+        ctx.arith, ctx.shape = arith, tuple(src_fea.shape)
+        return homo_warp_packed(packed[0], rt, depth_values, src_fea.shape[1], src_fea.shape[3], arith)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rt, depth_values = ctx.saved_tensors
+        return homo_warp_backward(rt, depth_values, grad_out, ctx.shape, ctx.arith), None, None, None
+
+
+def homo_warp_backward(rot_trans, depth_values: torch.Tensor, grad_out: torch.Tensor, src_shape,
+                       arith: Optional[str] = None) -> torch.Tensor:
+    """grad_out [B,C,D,H,W] -> grad_src [B,C,H,W]: the grid_sample scatter as a deterministic, atomic-free gather."""
+    lib = _lib.load()
+    dev = _need_cuda(depth_values, grad_out)
+    b, c, h, w = src_shape
+    d = depth_values.shape[1]
+    if tuple(grad_out.shape) != (b, c, d, h, w):
+        raise _lib.TmvsError(f"grad_out must be [{b},{c},{d},{h},{w}], got {list(grad_out.shape)}")
+    mode = _depth_mode(depth_values, b, h, w)
+    depth_values, grad_out = depth_values.contiguous(), grad_out.contiguous()
+    rt, rt_flag = _rt_arg(rot_trans, (b, 12), dev)
+    gsrc = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+    ws_bytes = lib.tmvs_homo_warp_bwd_workspace_bytes(b, c, d, h, w)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tmvs_homo_warp_bwd(ctypes.c_void_p(rt.data_ptr()), _ptr(depth_values), mode, _ptr(grad_out), _ptr(gsrc),
+                                    _ptr(ws), ws_bytes, b, c, d, h, w, _flags(arith, rt_flag), _stream())
+    _lib.check(rc, "tmvs_homo_warp_bwd")
+    return gsrc
+
+
 def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
-                 depth_values: torch.Tensor) -> torch.Tensor:
-    """Drop-in for models/module.py:284-322 (forward only; the fused path carries the autograd).
+                 depth_values: torch.Tensor, arith: Optional[str] = None) -> torch.Tensor:
+    """Drop-in for models/module.py:284-322, differentiable wrt src_fea like the reference.
 
     src_fea [B,C,H,W]; src_proj, ref_proj [B,4,4]; depth_values [B,D] or [B,D,H,W] -> [B,C,D,H,W].
-    Raises when a gradient would have to flow through the warped volume (training with only this function patched):
-    the volume's general gradient does not have the rank-1 form the fused backward exploits, and returning a detached
-    tensor would silently zero the feature gradients.  Training goes through cost_volume / DepthNet (patch_reference).
+    The 4x4 algebra runs with the reference's torch ops on the device the projections live on and its result is
+    handed to the kernel where it is (no host round trip).  Training through this function alone materialises the
+    warped volume and its gradient, as the reference does; the fused cost_volume / DepthNet path never forms either.
     """
     _need_cuda(src_fea, depth_values)
-    if torch.is_grad_enabled() and (src_fea.requires_grad or depth_values.requires_grad):
-        raise _lib.TmvsError("homo_warping is forward-only: for training use transmvsnet_b200.cost_volume / DepthNet "
-                             "(patch_reference), whose autograd runs the atomic-free backward kernels")
+    if depth_values.shape[0] != src_fea.shape[0]:
+        raise _lib.TmvsError(f"depth_values has batch {depth_values.shape[0]}, src_fea {src_fea.shape[0]}")
     with torch.no_grad():
         rt = relative_rot_trans(src_proj.float(), ref_proj.float())
+    if torch.is_grad_enabled() and src_fea.requires_grad:
+        return _HomoWarp.apply(src_fea, rt, depth_values.detach(), arith)
+    with torch.no_grad():
         packed = pack_sources([src_fea.detach()])
-        return homo_warp_packed(packed[0], rt, depth_values.detach(), src_fea.shape[1], src_fea.shape[3])
+        return homo_warp_packed(packed[0], rt, depth_values.detach(), src_fea.shape[1], src_fea.shape[3], arith)
 
 
-def cost_volume_packed(ref_fea: torch.Tensor, packed: torch.Tensor, rot_trans, depth_values: torch.Tensor,
-                       view_weights: Optional[torch.Tensor], want_views: bool, want_agg: bool
+def cost_volume_packed(ref_fea: torch.Tensor, packed, rot_trans, depth_values: torch.Tensor,
+                       view_weights: Optional[torch.Tensor], want_views: bool, want_agg: bool,
+                       arith: Optional[str] = None, vw_shift: int = 0
                        ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """packed: pack_sources() of the N source maps [N,B,H,Wb,C4,8,4], or a list of N per-view packed maps
+    [B,H,Wb,C4,8,4] living anywhere on the device (a scan-level cache).  vw_shift: view_weights are given at the
+    resolution of a coarser stage [B,N,ceil(H/2^s),ceil(W/2^s)] and read as their nearest-x2 upsampling
+    (models/TransMVSNet.py:193-194) without materialising it."""
     lib = _lib.load()
-    dev = _need_cuda(ref_fea, packed, depth_values, view_weights)
+    per_view = isinstance(packed, (list, tuple))
+    dev = _need_cuda(ref_fea, depth_values, view_weights, *(packed if per_view else [packed]))
     b, c, h, w = ref_fea.shape
-    n = packed.shape[0]
+    n = len(packed) if per_view else packed.shape[0]
+    if per_view:
+        for pv in packed:
+            _check_packed(pv, None, b, c, h, w)
+    else:
+        _check_packed(packed, n, b, c, h, w)
+    if depth_values.shape[0] != b:
+        raise _lib.TmvsError(f"depth_values has batch {depth_values.shape[0]}, the features {b}")
     d = depth_values.shape[1]
     mode = _depth_mode(depth_values, b, h, w)
     depth_values = depth_values.contiguous()
-    rt = _host_rt(rot_trans)
-    if tuple(rt.shape) != (n, b, 12):
-        raise _lib.TmvsError(f"rot_trans must be [{n},{b},12], got {tuple(rt.shape)}")
+    rt, rt_flag = _rt_arg(rot_trans, (n, b, 12), dev)
+    vw_h, vw_w = h, w
     if want_agg:
         if view_weights is None:
             raise _lib.TmvsError("aggregation needs view_weights")
-        if tuple(view_weights.shape) != (b, n, h, w):
-            raise _lib.TmvsError(f"view_weights must be [{b},{n},{h},{w}], got {tuple(view_weights.shape)}")
+        sh = 1 << vw_shift
+        vw_h, vw_w = (h + sh - 1) // sh, (w + sh - 1) // sh
+        if view_weights.dim() != 4 or tuple(view_weights.shape[:2]) != (b, n) or view_weights.shape[2] < vw_h \
+                or view_weights.shape[3] < vw_w or (vw_shift == 0 and tuple(view_weights.shape[2:]) != (h, w)):
+            raise _lib.TmvsError(f"view_weights must be [{b},{n},{vw_h},{vw_w}] (vw_shift={vw_shift}), "
+                                 f"got {tuple(view_weights.shape)}")
         view_weights = view_weights.contiguous()
+        vw_h, vw_w = view_weights.shape[2], view_weights.shape[3]
     views = torch.empty((n, b, d, h, w), dtype=torch.float32, device=dev) if want_views else None
     agg = torch.empty((b, d, h, w), dtype=torch.float32, device=dev) if want_agg else None
     rb, rc_, rh, rw = ref_fea.stride()
+    flags = _flags(arith, rt_flag)
     with torch.cuda.device(dev):
-        rc = lib.tmvs_costvol_fwd(_ptr(ref_fea), rb, rc_, rh, rw, _ptr(packed), ctypes.c_void_p(rt.data_ptr()),
-                                  _ptr(depth_values), mode, _ptr(view_weights if want_agg else None), _ptr(views),
-                                  _ptr(agg), b, c, d, h, w, n, _stream())
+        if per_view or vw_shift:
+            ptrs = (ctypes.c_void_p * n)(*[(packed[i] if per_view else packed[i]).data_ptr() for i in range(n)])
+            rc = lib.tmvs_costvol_fwd_cached(_ptr(ref_fea), rb, rc_, rh, rw, ctypes.cast(ptrs, ctypes.c_void_p),
+                                             ctypes.c_void_p(rt.data_ptr()), _ptr(depth_values), mode,
+                                             _ptr(view_weights if want_agg else None), vw_shift, vw_h, vw_w,
+                                             _ptr(views), _ptr(agg), b, c, d, h, w, n, flags, _stream())
+        else:
+            rc = lib.tmvs_costvol_fwd(_ptr(ref_fea), rb, rc_, rh, rw, _ptr(packed), ctypes.c_void_p(rt.data_ptr()),
+                                      _ptr(depth_values), mode, _ptr(view_weights if want_agg else None), _ptr(views),
+                                      _ptr(agg), b, c, d, h, w, n, flags, _stream())
     _lib.check(rc, "tmvs_costvol_fwd")
     return agg, views
 
@@ -206,6 +336,10 @@ def depth_hypotheses(cur_depth: torch.Tensor, ndepth: int, depth_interval_pixel:
     dev = _need_cuda(cur_depth)
     cur = cur_depth.detach().contiguous()
     b = cur.shape[0]
+    if image_hw[0] % stage_scale or image_hw[1] % stage_scale:
+        # the kernel blends the two centre pixels with weight 1/2, which is what F.interpolate(align_corners=False)
+        # does only for an integer ratio (models/TransMVSNet.py:202-204)
+        raise _lib.TmvsError(f"image size {tuple(image_hw)} is not divisible by the stage scale {stage_scale}")
     h, w = image_hw[0] // stage_scale, image_hw[1] // stage_scale
     out = torch.empty((b, ndepth, h, w), dtype=torch.float32, device=dev)
     planes, hp, wp = (cur.shape[1], 0, 0) if cur.dim() == 2 else (0, cur.shape[1], cur.shape[2])
@@ -276,26 +410,33 @@ def pixelwise_aggregate(sim_views: torch.Tensor, folded_mlp: torch.Tensor) -> Tu
 
 
 def costvol_backward_packed(ref_fea: torch.Tensor, packed: torch.Tensor, rot_trans, depth_values: torch.Tensor,
-                            grad_views: torch.Tensor, need_ref: bool = True, need_src: bool = True
+                            grad_views: torch.Tensor, need_ref: bool = True, need_src: bool = True,
+                            arith: Optional[str] = None, extra: int = 0
                             ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """dL/d sim_i [N,B,D,H,W] -> (grad_ref [B,C,H,W], grad_src [N,B,C,H,W]); deterministic, no fp atomics."""
     lib = _lib.load()
     dev = _need_cuda(ref_fea, packed, depth_values, grad_views)
     b, c, h, w = ref_fea.shape
     n = packed.shape[0]
+    _check_packed(packed, n, b, c, h, w)
+    if depth_values.shape[0] != b:
+        raise _lib.TmvsError(f"depth_values has batch {depth_values.shape[0]}, the features {b}")
     d = depth_values.shape[1]
+    if tuple(grad_views.shape) != (n, b, d, h, w):
+        raise _lib.TmvsError(f"grad_views must be [{n},{b},{d},{h},{w}], got {list(grad_views.shape)}")
     mode = _depth_mode(depth_values, b, h, w)
     depth_values, grad_views = depth_values.contiguous(), grad_views.contiguous()
-    rt = _host_rt(rot_trans)
+    rt, rt_flag = _rt_arg(rot_trans, (n, b, 12), dev)
+    flags = _flags(arith, rt_flag | extra)
     gref = torch.empty((b, c, h, w), dtype=torch.float32, device=dev) if need_ref else None
     gsrc = torch.empty((n, b, c, h, w), dtype=torch.float32, device=dev) if need_src else None
-    ws_bytes = lib.tmvs_costvol_bwd_workspace_bytes(b, c, d, h, w, n)
+    ws_bytes = lib.tmvs_costvol_bwd_workspace_bytes(b, c, d, h, w, n, flags)
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     rb, rc_, rh, rw = ref_fea.stride()
     with torch.cuda.device(dev):
         rc = lib.tmvs_costvol_bwd(_ptr(ref_fea), rb, rc_, rh, rw, _ptr(packed), ctypes.c_void_p(rt.data_ptr()),
                                   _ptr(depth_values), mode, _ptr(grad_views), _ptr(gref), _ptr(gsrc), _ptr(ws),
-                                  ws_bytes, b, c, d, h, w, n, _stream())
+                                  ws_bytes, b, c, d, h, w, n, flags, _stream())
     _lib.check(rc, "tmvs_costvol_bwd")
     return gref, gsrc
 
@@ -304,13 +445,18 @@ class _CostVolume(torch.autograd.Function):
     """Fused cost volume with autograd to the features: saves the inputs, never the volume."""
 
     @staticmethod
-    def forward(ctx, rot_trans, depth_values, view_weights, want_views, ref_fea, *src_feas):
+    def forward(ctx, rot_trans, depth_values, view_weights, want_views, arith, ref_fea, *src_feas):
+        for s in src_feas:
+            if s.shape != ref_fea.shape:
+                raise _lib.TmvsError(f"source features {list(s.shape)} do not match the reference {list(ref_fea.shape)}")
         packed = pack_sources([s.detach() for s in src_feas])
         want_agg = view_weights is not None
+        arith = _ARITH.get() if arith is None else arith       # the backward may run in another context
         agg, views = cost_volume_packed(ref_fea.detach(), packed, rot_trans, depth_values.detach(),
                                         None if view_weights is None else view_weights.detach(),
-                                        want_views, want_agg)
+                                        want_views, want_agg, arith)
         ctx.rot_trans = rot_trans
+        ctx.arith = arith
         ctx.has_agg, ctx.has_views = want_agg, want_views
         ctx.save_for_backward(ref_fea.detach(), packed, depth_values.detach(),
                               None if view_weights is None else view_weights.detach())
@@ -340,17 +486,17 @@ class _CostVolume(torch.autograd.Function):
             if g is not None:
                 grad_views = g if grad_views is None else grad_views + g
         if grad_views is None:
-            return (None,) * (5 + n)
-        need_ref = ctx.needs_input_grad[4]
-        need_src = any(ctx.needs_input_grad[5:])
+            return (None,) * (6 + n)
+        need_ref = ctx.needs_input_grad[5]
+        need_src = any(ctx.needs_input_grad[6:])
         gref, gsrc = costvol_backward_packed(ref_fea, packed, ctx.rot_trans, depth_values, grad_views.contiguous(),
-                                             need_ref, need_src)
-        src_grads = [gsrc[i] if (need_src and ctx.needs_input_grad[5 + i]) else None for i in range(n)]
-        return (None, None, None, None, gref, *src_grads)
+                                             need_ref, need_src, ctx.arith)
+        src_grads = [gsrc[i] if (need_src and ctx.needs_input_grad[6 + i]) else None for i in range(n)]
+        return (None, None, None, None, None, gref, *src_grads)
 
 
 def cost_volume(ref_fea: torch.Tensor, src_feas: Sequence[torch.Tensor], rot_trans, depth_values: torch.Tensor,
-                view_weights: Optional[torch.Tensor] = None, want_views: bool = False
+                view_weights: Optional[torch.Tensor] = None, want_views: bool = False, arith: Optional[str] = None
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused view loop of DepthNet.forward (models/TransMVSNet.py:71-93).
 
@@ -363,9 +509,9 @@ def cost_volume(ref_fea: torch.Tensor, src_feas: Sequence[torch.Tensor], rot_tra
         raise _lib.TmvsError("cost_volume: nothing to compute (no view_weights and want_views=False)")
     if want_agg and view_weights.requires_grad and torch.is_grad_enabled():
         # learned weights in the graph (stage-1 training): keep them differentiable
-        _, views = cost_volume(ref_fea, src_feas, rot_trans, depth_values, None, True)
+        _, views = cost_volume(ref_fea, src_feas, rot_trans, depth_values, None, True, arith)
         return aggregate(views, view_weights), (views if want_views else None)
-    outs = _CostVolume.apply(rot_trans, depth_values, view_weights, want_views, ref_fea, *src_feas)
+    outs = _CostVolume.apply(rot_trans, depth_values, view_weights, want_views, arith, ref_fea, *src_feas)
     agg = outs[0] if want_agg else None
     views = outs[-1] if want_views else None
     return agg, views

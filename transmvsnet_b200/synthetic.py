@@ -38,10 +38,13 @@ class StageInputs:
     cur_depth: Optional[torch.Tensor] = None
     interval_pixel: float = 0.0
     image_hw: tuple = (0, 0)
+    # (B, D, h, w) of the stage; lean scan jobs carry no depth_values (generated on the device from cur_depth) and, past
+    # stage 1, no view_weights (the kernel reads stage 1's at its own resolution)
+    bdhw: tuple = ()
 
     @property
     def voxel_views(self) -> int:
-        b, d, h, w = self.depth_values.shape
+        b, d, h, w = self.bdhw if self.bdhw else self.depth_values.shape
         return b * d * h * w * (len(self.features) - 1)
 
 
@@ -113,8 +116,11 @@ def make_cameras(batch: int, n_views: int, height: int, width: int, *, kind: str
 def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 1152, width: int = 1600,
                kind: str = "dtu", seed: int = 0, channels: Optional[int] = None,
                num_depth: Optional[int] = None, cameras: Optional[Dict[str, torch.Tensor]] = None,
-               stage1_weights: Optional[torch.Tensor] = None) -> StageInputs:
-    """Synthetic inputs of cascade stage `stage` (1..3) for an image of (height, width)."""
+               stage1_weights: Optional[torch.Tensor] = None, features: Optional[List[torch.Tensor]] = None,
+               logits: Optional[torch.Tensor] = None, lean: bool = False) -> StageInputs:
+    """Synthetic inputs of cascade stage `stage` (1..3) for an image of (height, width).
+    features / logits: use these tensors instead of drawing new ones (a scan shares feature maps between views).
+    lean: leave out what the scan pipeline derives on the device (per-pixel hypotheses, upsampled view weights)."""
     c_def, d_def, scale = STAGES[stage - 1]
     c = channels or c_def
     d = num_depth or d_def
@@ -125,7 +131,10 @@ def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 11
     d_min, d_max = dv[:, 0], dv[:, -1]
     depth_interval = (d_max - d_min) / dv.shape[1]           # models/TransMVSNet.py:149
     cur_depth = dv
-    if stage == 1:
+    hyp = None
+    if stage == 1 and lean:
+        pass
+    elif stage == 1:
         # models/module.py:616-623 (2-D branch): the global range split into D planes
         new_int = (d_max - d_min) / (d - 1)
         hyp = d_min[:, None] + torch.arange(d, dtype=torch.float32)[None] * new_int[:, None]
@@ -138,34 +147,40 @@ def make_stage(stage: int, *, batch: int = 1, n_views: int = 5, height: int = 11
         mid = (d_min + 0.5 * (d_max - d_min))[:, None, None]
         surf = mid + 0.25 * span * torch.sin(3.0 * math.pi * xx) * torch.cos(2.0 * math.pi * yy)[None] \
             + 0.1 * span * (xx - 0.5)[None]
-        ipx = (DEPTH_RATIOS[stage - 1] * depth_interval)[:, None, None]
-        cur_min = surf - d / 2 * ipx
-        cur_max = surf + d / 2 * ipx
-        new_int = (cur_max - cur_min) / (d - 1)
-        hyp = cur_min[:, None] + torch.arange(d, dtype=torch.float32)[None, :, None, None] * new_int[:, None]
-        hyp = hyp.contiguous()
+        if not lean:
+            ipx = (DEPTH_RATIOS[stage - 1] * depth_interval)[:, None, None]
+            cur_min = surf - d / 2 * ipx
+            cur_max = surf + d / 2 * ipx
+            new_int = (cur_max - cur_min) / (d - 1)
+            hyp = cur_min[:, None] + torch.arange(d, dtype=torch.float32)[None, :, None, None] * new_int[:, None]
+            hyp = hyp.contiguous()
         # the same surface at the previous stage's resolution: what the cascade would carry over
         hp, wp = height // STAGES[stage - 2][2], width // STAGES[stage - 2][2]
         yy = torch.linspace(0, 1, hp)[:, None]
         xx = torch.linspace(0, 1, wp)[None, :]
         cur_depth = (mid + 0.25 * span * torch.sin(3.0 * math.pi * xx) * torch.cos(2.0 * math.pi * yy)[None]
                      + 0.1 * span * (xx - 0.5)[None]).float().contiguous()
-    feats = [torch.randn(batch, c, h, w, generator=g) for _ in range(n_views)]
+    feats = features if features is not None else [torch.randn(batch, c, h, w, generator=g) for _ in range(n_views)]
     if stage1_weights is None:
         h1, w1 = height // STAGES[0][2], width // STAGES[0][2]
         gw = torch.Generator().manual_seed(seed * 1000 + 17)
         stage1_weights = torch.sigmoid(torch.randn(batch, n_views - 1, h1, w1, generator=gw))
     vw = stage1_weights
-    for _ in range(stage - 1):                               # models/TransMVSNet.py:193-194
-        vw = torch.nn.functional.interpolate(vw, scale_factor=2, mode="nearest")
-    if vw.shape[2] < h or vw.shape[3] < w:                   # sizes not divisible by the stage scales
-        vw = torch.sigmoid(torch.randn(batch, n_views - 1, h, w, generator=g))
-    vw = vw[:, :, :h, :w].contiguous()
-    logits = 3.0 * torch.randn(batch, d, h, w, generator=g)
+    if lean:
+        vw = stage1_weights if stage == 1 else None
+    else:
+        for _ in range(stage - 1):                           # models/TransMVSNet.py:193-194
+            vw = torch.nn.functional.interpolate(vw, scale_factor=2, mode="nearest")
+        if vw.shape[2] < h or vw.shape[3] < w:               # sizes not divisible by the stage scales
+            vw = torch.sigmoid(torch.randn(batch, n_views - 1, h, w, generator=g))
+        vw = vw[:, :, :h, :w].contiguous()
+    if logits is None:
+        logits = 3.0 * torch.randn(batch, d, h, w, generator=g)
     return StageInputs(stage=stage, features=feats, proj_matrix=cams[f"stage{stage}"],
-                       depth_values=hyp.float(), view_weights=vw, logits=logits, num_depth=d,
+                       depth_values=None if hyp is None else hyp.float(), view_weights=vw, logits=logits, num_depth=d,
                        cur_depth=cur_depth.float().contiguous(),
-                       interval_pixel=float(DEPTH_RATIOS[stage - 1] * depth_interval[0]), image_hw=(height, width))
+                       interval_pixel=float(DEPTH_RATIOS[stage - 1] * depth_interval[0]), image_hw=(height, width),
+                       bdhw=(batch, d, h, w))
 
 
 def make_cascade(*, batch: int = 1, n_views: int = 5, height: int = 1152, width: int = 1600,
@@ -174,6 +189,62 @@ def make_cascade(*, batch: int = 1, n_views: int = 5, height: int = 1152, width:
     cams = make_cameras(batch, n_views, height, width, kind=kind, seed=seed)
     return [make_stage(s, batch=batch, n_views=n_views, height=height, width=width, kind=kind,
                        seed=seed, cameras=cams) for s in (1, 2, 3)]
+
+
+@dataclass
+class ScanInputs:
+    """One scan as the reference's test loop walks it (datasets/general_eval.py:25-57, 133-138): V views, and for
+    every view taken as the reference view its N-1 source views from the pairing.  A view's feature pyramid is ONE
+    set of tensors, shared by every job it appears in (as reference view once, as source view N-1 times)."""
+    pyramids: List[List[torch.Tensor]]                 # [view][stage] -> [1,C,h,w]
+    pairs: List[tuple]                                 # (ref_view, [src_views])  -- the pair.txt of the scan
+    jobs: List[List[StageInputs]]                      # [job][stage]; StageInputs.features alias the pyramids
+
+    @property
+    def voxel_views(self) -> int:
+        return sum(st.voxel_views for job in self.jobs for st in job)
+
+
+def scan_pairs(n_scan_views: int, n_views: int) -> List[tuple]:
+    """Synthetic pair.txt: the N-1 nearest views on a ring (v+1, v-1, v+2, v-2, ...), so that -- as in DTU's pairing --
+    every view is a source view of N-1 reference views."""
+    pairs = []
+    for v in range(n_scan_views):
+        srcs, k = [], 1
+        while len(srcs) < n_views - 1:
+            for cand in ((v + k) % n_scan_views, (v - k) % n_scan_views):
+                if len(srcs) < n_views - 1 and cand != v and cand not in srcs:
+                    srcs.append(cand)
+            k += 1
+            if k > n_scan_views:                      # tiny scans: repeat the first source (general_eval.py:47-49)
+                srcs += [srcs[0]] * (n_views - 1 - len(srcs))
+        pairs.append((v, srcs))
+    return pairs
+
+
+def make_scan(n_scan_views: int = 49, *, n_views: int = 5, height: int = 1152, width: int = 1600, kind: str = "dtu",
+              seed: int = 0, logits_pool: int = 4, lean: bool = True) -> ScanInputs:
+    """A synthetic scan of `n_scan_views` views (DTU: 49) with the ring pairing above.  Feature pyramids are distinct per
+    view (a rolled copy of one random pyramid: distinct bytes at the cost of a memcpy); every job has its own cameras,
+    depth seeds and stage-1 view weights; the stand-in logits cycle through a pool of `logits_pool` distinct sets."""
+    g = torch.Generator().manual_seed(seed * 7 + 3)
+    base = [torch.randn(1, c, height // sc, width // sc, generator=g) for c, _, sc in STAGES]
+    pyramids = [[torch.roll(m, shifts=(3 * v + 1, 7 * v + 1), dims=(2, 3)).contiguous() if v else m for m in base]
+                for v in range(n_scan_views)]
+    pool = [[3.0 * torch.randn(1, d, height // sc, width // sc, generator=g) for _, d, sc in STAGES]
+            for _ in range(max(1, min(logits_pool, n_scan_views)))]
+    pairs = scan_pairs(n_scan_views, n_views)
+    jobs = []
+    h1, w1 = height // STAGES[0][2], width // STAGES[0][2]
+    for j, (ref, srcs) in enumerate(pairs):
+        cams = make_cameras(1, n_views, height, width, kind=kind, seed=seed * 1000 + j)
+        ids = [ref] + srcs
+        w1s = torch.sigmoid(torch.randn(1, n_views - 1, h1, w1, generator=g))       # this job's stage-1 view weights
+        jobs.append([make_stage(s, batch=1, n_views=n_views, height=height, width=width, kind=kind, seed=seed * 1000 + j,
+                                cameras=cams, features=[pyramids[v][s - 1] for v in ids], logits=pool[j % len(pool)][s - 1],
+                                stage1_weights=w1s, lean=lean)
+                     for s in (1, 2, 3)])
+    return ScanInputs(pyramids=pyramids, pairs=pairs, jobs=jobs)
 
 
 def make_fusion_scene(n_views: int = 5, height: int = 64, width: int = 96, seed: int = 0, hole_fraction: float = 0.05,
