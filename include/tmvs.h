@@ -68,6 +68,8 @@ typedef void *tmvs_stream_t;
                                          it applies; same results up to fp32 re-association; measured slower */
 #define TMVS_F_BWD_SCAN        0x8u   /* tmvs_costvol_bwd: grad_src through the tile-scan kernels only (no cell tables) */
 #define TMVS_F_PACK_LDG        0x10u  /* tmvs_pack_sources: register-transpose kernel instead of the TMA engine */
+#define TMVS_F_FWD_SPLIT       0x20u  /* tmvs_costvol_fwd, C = 32: two channel passes of 16 (64 registers, 4 CTAs per SM) instead of
+                                         one pass over all 32 (128 registers, 2 CTAs per SM); measured slower */
 #define TMVS_F_TABLE_MB(mb)    ((unsigned)(mb) << 16)   /* tmvs_costvol_bwd(+_workspace_bytes): cap of the cell-table
                                          workspace in MiB (0 = default 3072), e.g. to exercise the multi-pass path */
 

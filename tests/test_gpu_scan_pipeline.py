@@ -127,3 +127,20 @@ def test_process_scan_equals_the_per_view_cascade():
     pyr = sum(m.numel() * 4 for m in scan.pyramids[0])
     per_job = sum((st.logits.numel() + st.cur_depth.numel()) * 4 for st in scan.jobs[0]) + scan.jobs[0][0].view_weights.numel() * 4
     assert pipe.h2d_bytes == 7 * (pyr + per_job)
+
+
+def test_channel_pass_kernel_agrees_with_the_one_pass_kernel():
+    """C = 32 can run in two channel passes of 16 (TMVS_F_FWD_SPLIT: 64 registers, 4 CTAs per SM; measured slower, so
+    opt-in) instead of one pass over all 32.  Same taps, same weights; only the channel sum is re-associated: <= 2e-6 of the range, for
+    the aggregated and the per-view outputs, per-pixel and per-plane hypotheses, ragged sizes and the image rim."""
+    from transmvsnet_b200 import _lib
+    for hw, batch in (((96, 160), 2), ((148, 204), 1)):
+        st = synthetic.make_stage(1, batch=batch, n_views=4, height=hw[0], width=hw[1], seed=51)
+        rt = geometry.stage_rot_trans(st.proj_matrix)
+        for dv in (st.depth_values, st.depth_values[:, :, 0, 0].contiguous()):
+            args = (cu(st.features[0]), [cu(f) for f in st.features[1:]], rt, cu(dv), cu(st.view_weights))
+            agg_1, views_1 = tm.cost_volume(*args, want_views=True)
+            with ops.extra_flags(_lib.F_FWD_SPLIT):
+                agg_s, views_s = tm.cost_volume(*args, want_views=True)
+            for a, b in ((agg_s, agg_1), (views_s, views_1)):
+                assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
