@@ -75,6 +75,7 @@ def voxel_views(stages) -> int:
 def make_config(workload: dict, vv: int, world: int, gather: str) -> dict:
     """The `config` object of the JSON line -- the same for both arms (the reference arm times the same workload)."""
     how = {"peer": ", depth+conf maps written by the read-out kernel into rank 0's buffer over NVLink peer memory",
+           "copy": ", depth+conf maps pushed into rank 0's peer-mapped buffer by the DMA engines over NVLink (side stream)",
            "nccl": ", NCCL all_gather of depth+conf", "": ""}[gather if world > 1 else ""]
     return {"workload": workload["name"], "voxel_views_per_step": vv,
             "l2": "inputs larger than L2 (>= 1 GB touched per step)", "view_weights": "given as inputs",
@@ -200,7 +201,7 @@ def run_reference_arm(args, workload):
         "impl": "reference", "metric": "cost_volume_voxel_views_per_s", "value": value, "unit": "voxel-views/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(workload, vv, args.gpus, "peer"),
+        "config": make_config(workload, vv, args.gpus, os.environ.get("TMVS_GATHER", "copy")),
         "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxel-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -333,8 +334,11 @@ def run_tmvs_arm(args, workload):
     # Multi-GPU: the stage-3 depth + confidence maps of every view end up on rank 0.  Default transport: the read-out
     # kernel writes them straight into rank 0's buffer through NVLink peer memory (sharding.PeerMapSink) -- no
     # collective, no extra kernel.  TMVS_GATHER=nccl keeps the NCCL all_gather on a side stream instead.
-    use_peer = world > 1 and workload["batch"] == 1 and os.environ.get("TMVS_GATHER", "peer") == "peer"
-    comm = torch.cuda.Stream() if (world > 1 and not use_peer) else None
+    # TMVS_GATHER: "copy" (default) = the maps are pushed into rank 0's peer-mapped buffer by the DMA engines on a side
+    # stream; "peer" = the read-out kernel stores them there itself (round 1's default); "nccl" = all_gather.
+    gather = os.environ.get("TMVS_GATHER", "copy")
+    use_peer = world > 1 and workload["batch"] == 1 and gather in ("peer", "copy")
+    comm = torch.cuda.Stream() if world > 1 else None
     sink = None
     if use_peer:
         h3, w3 = host[-1].depth_values.shape[2:]
@@ -346,14 +350,20 @@ def run_tmvs_arm(args, workload):
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok.item()) == 0.0:
-            sink, use_peer = None, False
-            comm = torch.cuda.Stream()
+            sink, use_peer, gather = None, False, "nccl"
     step_no = [0]
 
     def step():
         if sink is not None:    # ring of two step-slots per rank: this step's maps land in slot (parity, rank)
-            outs = pipeline.run_cascade(dev_stages, out_maps=sink.slot((step_no[0] & 1) * world + rank))
+            slot = (step_no[0] & 1) * world + rank
             step_no[0] += 1
+            if gather == "peer":
+                return pipeline.run_cascade(dev_stages, out_maps=sink.slot(slot))
+            outs = pipeline.run_cascade(dev_stages)
+            ready = torch.cuda.Event()
+            ready.record()
+            comm.wait_event(ready)
+            sink.push(slot, outs[-1]["depth"], outs[-1]["photo_confidence"], comm)
             return outs
         outs = pipeline.run_cascade(dev_stages)
         if world > 1:       # gather this view's stage-3 depth + confidence on rank 0, off the compute stream
@@ -517,7 +527,7 @@ def run_tmvs_arm(args, workload):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "ms_per_ref_view": elapsed_ms / args.steps / workload["batch"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": make_config(workload, vv, world, "peer" if use_peer else "nccl"),
+            "config": make_config(workload, vv, world, gather if use_peer else "nccl"),
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "workloads": extra,
             "clocks": sampler.summary(),
         }

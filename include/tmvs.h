@@ -85,6 +85,9 @@ int tmvs_version(void);
 int tmvs_peer_buffer_create(size_t bytes, void **ptr, unsigned char *handle64);   /* zero-filled, current device */
 int tmvs_peer_buffer_open(const unsigned char *handle64, void **ptr);             /* in another process of the box */
 int tmvs_peer_buffer_release(void *ptr, int owner);                               /* owner: cudaFree, else IPC close */
+/* Asynchronous copy (DMA engines, not SMs) from local device memory into a buffer opened with tmvs_peer_buffer_open:
+ * the transport for the maps when the producing kernel should not wait on the NVLink port. */
+int tmvs_peer_copy_async(void *dst, const void *src, size_t bytes, tmvs_stream_t stream);
 const char *tmvs_error_string(int code);
 
 /* Bytes of the packed source workspace for the given shape. */
@@ -198,14 +201,20 @@ int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float
  * SURVEY.md 8(f) N4 -- fusibile depth-map fusion (gipuma/fusibile/fusibile.cu:89-173 kernel `fusibile`, :175-210
  * copy_pc_to_host, :216-285 the per-camera launch / synchronise / host-scan loop; main.cpp:128-147 image set-up).
  *   images  [V][H][W][4] fp32: b, g, r in [0,1] and w = depth (425 + 512 * alpha/255, main.cpp:137); sampled through
- *           the texture unit with the reference's settings (float4, bilinear, unnormalised + 0.5).  512-byte aligned,
- *           W even and H*W a multiple of 32 (pitch-linear texture resources), else TMVS_E_UNSUPPORTED.
+ *           the texture unit with the reference's settings (float4 cudaArray per view, bilinear, unnormalised + 0.5:
+ *           main.cpp:30-66 -- each view is copied into an array this call allocates and frees).  16-byte aligned.
  *   cams    HOST [V][TMVS_FUSE_CAM_FLOATS]: P (3x4 row major), RK_inv = inverse(P[:, :3]) (3x3), camera centre C (3),
  *           P[:, 3] (3), focal length K[0] of the decomposed P (cameraGeometryUtils.h:104-156).
  *   depth_threshold 0.25, consistent_threshold 3 (algorithmparameters.h:11-12).
- *   carry_over != 0 reproduces the reference's output exactly: its per-pixel point buffer is never cleared between
+ *   carry_over bit 0 set reproduces the reference's output exactly: its per-pixel point buffer is never cleared between
  *           cameras, so every later camera re-emits a pixel's latest fused point (fusibile.cu:165-166,188);
- *           0 emits each camera's own points only.
+ *           clear: each camera's own points only.  Bit 1 (TMVS_FUSE_PITCH_LINEAR): sample pitch-linear textures over the
+ *           caller's buffer instead (no copy; needs 512-byte alignment, W even, H*W a multiple of 32).  The texture
+ *           two resource types give identical samples on B200).  Bit 2 (TMVS_FUSE_IEEE): IEEE division and square root.
+ *           The default arithmetic is the reference's AS ITS OWN BUILD COMPILES IT (CMakeLists.txt:10 --use_fast_math:
+ *           reciprocal-multiply divisions, MUFU.SQRT, the compiler's FMA contraction order), read off the SASS of
+ *           gipuma/fusibile/fusibile.cu; TMVS_FUSE_IEEE is the same source without --use_fast_math.  Both are pinned
+ *           bit for bit against the reference's compiled kernel (oracle/_ref, tests/test_gpu_fusion.py).
  *   points  [capacity][8] fp32 out: x, y, z, 0, b, g, r, 0 (point_cloud.h:7-11; the reference's float4 operator+ drops w),
  *           in the reference's order (camera, then y, then x).  *n_points (device, int64) = number of points found,
  *           which may exceed capacity (only the first `capacity` are written).
@@ -213,6 +222,8 @@ int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float
  */
 #define TMVS_FUSE_CAM_FLOATS 28
 #define TMVS_FUSE_MAX_VIEWS 1024       /* config.h:2 MAX_IMAGES */
+#define TMVS_FUSE_PITCH_LINEAR 2
+#define TMVS_FUSE_IEEE 4
 int tmvs_fusibile_fwd(const float *images, const float *cams, int V, int H, int W, float depth_threshold,
                       int consistent_threshold, int carry_over, float *points, long long capacity,
                       long long *n_points, void *workspace, size_t workspace_bytes, tmvs_stream_t stream);
@@ -220,7 +231,8 @@ size_t tmvs_fusibile_workspace_bytes(int V, int H, int W);
 /* Diagnostic: out[j] = tex2D<float4>(image, uv[j]) through the texture set-up tmvs_fusibile_fwd uses (image [H][W][4],
  * uv [n][2] unnormalised texture coordinates, out [n][4], all device).  The tests use it to measure the CPU oracle's
  * emulation of the hardware's 9-bit-weight bilinear filter.  Synchronises `stream`. */
-int tmvs_fusibile_tex_probe(const float *image, int H, int W, const float *uv, float *out, int n, tmvs_stream_t stream);
+int tmvs_fusibile_tex_probe(const float *image, int H, int W, const float *uv, float *out, int n, int mode,
+                            tmvs_stream_t stream);      /* mode: 0 = array texture, TMVS_FUSE_PITCH_LINEAR */
 
 /*
  * Backward of the cost volume wrt the features (autograd of models/module.py:318-320 and

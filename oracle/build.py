@@ -8,6 +8,8 @@
   and never enters the history.  Users: tests/test_gpu_dropin_reference.py (the drop-in bound INTO the reference's own
   TransMVSNet.forward, patched against unpatched) and bench.py --impl reference (the reference's own functions on the
   host cores).  When /root/reference is absent (the GPU box) the staged copy is used as it is.
+* oracle/_ref/libfusibile_ref.so -- the reference's own depth-map fusion kernel (gipuma/fusibile/fusibile.cu), compiled
+  for sm_100a from where it lies (build_fusibile_ref); pins tmvs_fusibile_fwd in tests/test_gpu_fusion.py.
 """
 import os
 import shutil
@@ -30,6 +32,34 @@ def build_ref() -> str:
             if os.path.exists(src):
                 shutil.copyfile(src, os.path.join(dst, name))
     return dst if os.path.exists(os.path.join(dst, "module.py")) else ""
+
+
+FUSE_SRC = "/root/reference/gipuma/fusibile"
+FUSE_REF = os.path.join(REF_DIR, "libfusibile_ref.so")             # the reference's own flags: -O3 --use_fast_math
+FUSE_REF_IEEE = os.path.join(REF_DIR, "libfusibile_ref_ieee.so")   # the same source without --use_fast_math
+
+
+def build_fusibile_ref(force: bool = False) -> str:
+    """Compile the reference's OWN fusion kernel file (gipuma/fusibile/fusibile.cu, from where it lies) for sm_100a into
+    oracle/_ref/libfusibile_ref.so, behind oracle/fusibile_ref/harness.cu.  The reference's CMake build needs OpenCV;
+    the kernel file does not -- camera.h only pulls <opencv2/core/core.hpp> in for a host-side struct, for which
+    oracle/fusibile_ref/opencv2/core/core.hpp is a 15-line stand-in.  nvcc cross-compiles without a GPU; the library
+    travels to the GPU box with the snapshot.  Returns "" when neither the sources nor a built library are present."""
+    harness = os.path.join(HERE, "fusibile_ref", "harness.cu")
+    kernel = os.path.join(FUSE_SRC, "fusibile.cu")
+    if not os.path.exists(kernel):
+        return FUSE_REF if os.path.exists(FUSE_REF) else ""
+    newest = max(os.path.getmtime(harness), os.path.getmtime(kernel))
+    if not force and all(os.path.exists(f) and os.path.getmtime(f) >= newest for f in (FUSE_REF, FUSE_REF_IEEE)):
+        return FUSE_REF
+    os.makedirs(REF_DIR, exist_ok=True)
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+    # the reference's CUDA_NVCC_FLAGS (gipuma/fusibile/CMakeLists.txt:10) with the architecture replaced by sm_100a
+    for out, flags in ((FUSE_REF, ["-O3", "--use_fast_math"]), (FUSE_REF_IEEE, ["-O3"])):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", *flags, "-std=c++11", "-shared", "-Xcompiler", "-fPIC",
+               "-I", os.path.join(HERE, "fusibile_ref"), "-I", FUSE_SRC, harness, kernel, "-o", out]
+        subprocess.run(cmd, check=True)
+    return FUSE_REF
 
 
 def import_reference():
@@ -66,3 +96,4 @@ def build(force: bool = False) -> str:
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_ref() or "reference not staged (/root/reference absent)")
+    print(build_fusibile_ref(force="--force" in sys.argv) or "fusibile reference not built (/root/reference absent)")

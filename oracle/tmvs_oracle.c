@@ -379,15 +379,18 @@ void tmvs_oracle_pixelwise_weight(const float *sim, const float *w0, const float
 }
 
 /* ------------------------------------------------------------------------- */
-/* fusibile depth-map fusion.  PARITY UNPINNED: the        */
-/* reference is a CUDA + OpenCV program (gipuma/fusibile) that cannot be      */
-/* built or run in this container; this restates its algorithm.              */
+/* fusibile depth-map fusion, restated on the CPU.  The    */
+/* PIN of the GPU path is no longer this restatement but the reference's own */
+/* kernel file compiled for sm_100a (oracle/build.py build_fusibile_ref,     */
+/* tests/test_gpu_fusion.py: bit-identical); this C version remains the      */
+/* CPU-side checker (IEEE arithmetic, modelled texture filter).              */
 /*   fusibile.cu:89-173  kernel `fusibile` (one reference camera)            */
 /*   fusibile.cu:54-69   get_3dpoint_cu, :71-85 project_on_camera,           */
 /*   fusibile.cu:44-52   depth_convert_cu, :21-33 float4 operators (w := 0)  */
 /*   fusibile.cu:175-210 copy_pc_to_host (buffer never cleared: carry-over)  */
-/* nvcc's default -fmad=true contracts a*b + c*d + e*f to mul, fma, fma; the */
-/* same explicit sequence is used here (and in csrc/tmvs_fusion.cu).         */
+/* nvcc contracts m0*x + m1*y + m2*z to mul(m1,y), fma(m0,x,.), fma(m2,z,.)   */
+/* (read off the SASS of the reference's kernel); the same explicit sequence */
+/* is used here and in csrc/tmvs_fusion.cu (its TMVS_FUSE_IEEE arithmetic).  */
 /* The texture fetch (main.cpp:46-66: float4, cudaFilterModeLinear,          */
 /* unnormalised coordinates) is EMULATED from the CUDA programming guide's   */
 /* description of linear filtering (xB = x - 0.5, i = floor(xB), fractions in */
@@ -402,9 +405,9 @@ static void fuse_backproject(const float *cam, int px, int py, float depth, floa
     const float x = fmaf(depth, (float)px, -p34[0]);
     const float y = fmaf(depth, (float)py, -p34[1]);
     const float z = depth - p34[2];
-    X[0] = fmaf(m[2], z, fmaf(m[1], y, m[0] * x));
-    X[1] = fmaf(m[5], z, fmaf(m[4], y, m[3] * x));
-    X[2] = fmaf(m[8], z, fmaf(m[7], y, m[6] * x));
+    X[0] = fmaf(m[2], z, fmaf(m[0], x, m[1] * y));
+    X[1] = fmaf(m[5], z, fmaf(m[3], x, m[4] * y));
+    X[2] = fmaf(m[8], z, fmaf(m[6], x, m[7] * y));
 }
 
 static int fuse_clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
@@ -460,9 +463,9 @@ long long tmvs_oracle_fusibile(const float *images, const float *cams, int V, in
                 for (int i = 0; i < V && count < 2 * consistent_threshold; ++i) {
                     if (i == c) continue;
                     const float *cam = cams + (size_t)i * 28;
-                    const float tx = fmaf(cam[2], X[2], fmaf(cam[1], X[1], cam[0] * X[0])) + cam[3];
-                    const float ty = fmaf(cam[6], X[2], fmaf(cam[5], X[1], cam[4] * X[0])) + cam[7];
-                    const float tz = fmaf(cam[10], X[2], fmaf(cam[9], X[1], cam[8] * X[0])) + cam[11];
+                    const float tx = fmaf(cam[2], X[2], fmaf(cam[0], X[0], cam[1] * X[1])) + cam[3];
+                    const float ty = fmaf(cam[6], X[2], fmaf(cam[4], X[0], cam[5] * X[1])) + cam[7];
+                    const float tz = fmaf(cam[10], X[2], fmaf(cam[8], X[0], cam[9] * X[1])) + cam[11];
                     const float ptx = tx / tz, pty = ty / tz;
                     depth = tz;
                     if (ptx < 0 || ptx >= W || pty < 0 || pty >= H) continue;
@@ -470,7 +473,7 @@ long long tmvs_oracle_fusibile(const float *images, const float *cams, int V, in
                     fuse_tex_linear(images + (size_t)i * HW * 4, H, W, ptx + 0.5f, pty + 0.5f, tmp_T);
                     if ((double)tmp_T[3] <= 425.001) continue;
                     const float bx = ref[21] - cam[21], by = ref[22] - cam[22], bz = ref[23] - cam[23];
-                    const float baseline = sqrtf(fmaf(bz, bz, fmaf(by, by, bx * bx)));
+                    const float baseline = sqrtf(fmaf(bz, bz, fmaf(bx, bx, by * by)));
                     const float fb = ref[27] * baseline;
                     const float depth_disp = fb / depth, temp_disp = fb / tmp_T[3];
                     if (fabsf(depth_disp - temp_disp) < depth_threshold) {

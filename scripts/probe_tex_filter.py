@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transmvsnet_b200 import _lib  # noqa: E402
 
 DEV = torch.device("cuda:0")
+MODE = 2 if "--pitch-linear" in sys.argv else 0       # 0: cudaArray texture (the reference's), 2: pitch-linear
 h, w = 32, 64
 img = torch.zeros(h, w, 4)
 img[..., 0] = torch.arange(w)[None, :].float()
@@ -26,7 +27,7 @@ lib = _lib.load()
 uv_d = torch.from_numpy(uv).to(DEV)
 out = torch.empty((n, 4), device=DEV)
 rc = lib.tmvs_fusibile_tex_probe(ctypes.c_void_p(img.data_ptr()), h, w, ctypes.c_void_p(uv_d.data_ptr()),
-                                 ctypes.c_void_p(out.data_ptr()), n, None)
+                                 ctypes.c_void_p(out.data_ptr()), n, MODE, None)
 assert rc == 0
 r = out.cpu().numpy().astype(np.float64)
 res = {}
@@ -48,5 +49,6 @@ for ch in (2, 3):
 res["n"] = n
 print(json.dumps(res))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/probe_tex.json", "w"), indent=1)
-np.savez("gpurun_out/probe_tex.npz", img=img.cpu().numpy(), uv=uv, out=out.cpu().numpy())
+res["texture"] = "pitch-linear" if MODE else "cudaArray"
+json.dump(res, open(f"gpurun_out/probe_tex_{'pitch' if MODE else 'array'}.json", "w"), indent=1)
+np.savez(f"gpurun_out/probe_tex_{'pitch' if MODE else 'array'}.npz", img=img.cpu().numpy(), uv=uv, out=out.cpu().numpy())

@@ -68,7 +68,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.tmvs_fusibile_fwd(null, null, 4, 8, 8, 0.25, 3, 1, null, 16, null, null, 0, null) == -1
     assert lib.tmvs_fusibile_fwd(one, one, 1, 8, 8, 0.25, 3, 1, one, 16, one, one, 0, null) == -2        # one view: nothing to fuse
     assert lib.tmvs_fusibile_workspace_bytes(0, 8, 8) == 0 and lib.tmvs_fusibile_workspace_bytes(4, 8, 8) > 4 * 64 * 32
-    assert lib.tmvs_fusibile_tex_probe(null, 8, 8, one, one, 4, null) == -1
+    assert lib.tmvs_fusibile_tex_probe(null, 8, 8, one, one, 4, 0, null) == -1
     assert lib.tmvs_peer_buffer_create(0, null, null) == -1 and lib.tmvs_peer_buffer_open(null, null) == -1
     assert lib.tmvs_peer_buffer_release(null, 1) == -1
     assert lib.tmvs_costvol_bwd_workspace_bytes(1, 8, 8, 16, 24, 2, 0) > 0 and lib.tmvs_costvol_bwd_workspace_bytes(0, 8, 8, 16, 24, 2, 0) == 0

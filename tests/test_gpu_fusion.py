@@ -14,12 +14,12 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 
 
-def _probe(img: torch.Tensor, uv: np.ndarray) -> np.ndarray:
+def _probe(img: torch.Tensor, uv: np.ndarray, mode: int = 0) -> np.ndarray:
     lib = _lib.load()
     uv_d = torch.from_numpy(np.ascontiguousarray(uv, np.float32)).to(DEV)
     out = torch.empty((uv.shape[0], 4), dtype=torch.float32, device=DEV)
     rc = lib.tmvs_fusibile_tex_probe(ctypes.c_void_p(img.data_ptr()), img.shape[0], img.shape[1],
-                                     ctypes.c_void_p(uv_d.data_ptr()), ctypes.c_void_p(out.data_ptr()), uv.shape[0],
+                                     ctypes.c_void_p(uv_d.data_ptr()), ctypes.c_void_p(out.data_ptr()), uv.shape[0], mode,
                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "tmvs_fusibile_tex_probe")
     return out.cpu().numpy()
@@ -53,7 +53,7 @@ def test_fusion_matches_oracle(carry):
     images, Ps = synthetic.make_fusion_scene(n_views=6, height=96, width=128, seed=4)
     cams = fusion.camera_records(Ps.numpy())
     ref = oracle.fusibile(images, cams, carry_over=carry)
-    got = fusion.fuse_depth_maps(images.to(DEV), cams, carry_over=carry).cpu().numpy()
+    got = fusion.fuse_depth_maps(images.to(DEV), cams, carry_over=carry, ieee=True).cpu().numpy()   # the CPU restatement is IEEE
     assert len(ref) > 1000
     # borderline consistency decisions may flip where the texture unit and its model differ in the last bit
     assert abs(len(got) - len(ref)) <= max(2, len(ref) // 2000), (len(got), len(ref))
@@ -90,4 +90,51 @@ def test_fusion_edge_cases():
     with pytest.raises(_lib.TmvsError):
         fusion.fuse_depth_maps(images, cams)                                                   # CPU tensor: no fallback
     with pytest.raises(_lib.TmvsError):
-        fusion.fuse_depth_maps(dev_img[:, :, :63].contiguous(), cams)                          # odd width: texture pitch
+        fusion.fuse_depth_maps(dev_img[:, :, :63].contiguous(), cams, pitch_linear=True)       # odd width: texture pitch
+
+
+# ------------------------------------------------------------------------------- the pin: the reference's own kernel
+def _reference_fusibile(images: torch.Tensor, cams: np.ndarray, depth_threshold=0.25, consistent_threshold=3, ieee=False):
+    """gipuma/fusibile/fusibile.cu itself (kernel :89-173, copy_pc_to_host :175-210, per-camera loop :216-285), compiled
+    for sm_100a by oracle/build.py build_fusibile_ref() into oracle/_ref/libfusibile_ref.so."""
+    import os
+    from oracle import build as oracle_build
+    path = oracle_build.FUSE_REF_IEEE if ieee else oracle_build.FUSE_REF
+    if not os.path.exists(path):
+        pytest.fail("oracle/_ref/libfusibile_ref.so is missing: run __graft_entry__.build() in the build container")
+    lib = ctypes.CDLL(path)
+    lib.fusibile_ref_run.restype = ctypes.c_int
+    lib.fusibile_ref_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]
+    img = np.ascontiguousarray(images.cpu().numpy(), np.float32)
+    v, h, w, _ = img.shape
+    cams = np.ascontiguousarray(cams, np.float32)
+    cap = v * h * w
+    pts = np.zeros((cap, 8), np.float32)
+    n = ctypes.c_longlong(0)
+    rc = lib.fusibile_ref_run(img.ctypes.data, cams.ctypes.data, v, h, w, depth_threshold, consistent_threshold,
+                              pts.ctypes.data, cap, ctypes.byref(n))
+    assert rc == 0, rc
+    return pts[:n.value]
+
+
+@pytest.mark.parametrize("ieee", [False, True])
+@pytest.mark.parametrize("shape", [(6, 96, 128, 4), (9, 288, 400, 11), (5, 64, 96, 5), (4, 33, 45, 6)])
+def test_fusion_matches_the_reference_kernel(shape, ieee):
+    """tmvs_fusibile_fwd against the reference's OWN compiled kernel on the same GPU, same float4 images, same camera
+    records -- built with the reference's flags (-O3 --use_fast_math, the default arithmetic of the entry point) and
+    without --use_fast_math (TMVS_FUSE_IEEE): the same points, in the same order (camera, y, x), BIT FOR BIT."""
+    v, h, w, seed = shape
+    images, Ps = synthetic.make_fusion_scene(n_views=v, height=h, width=w, seed=seed)
+    cams = fusion.camera_records(Ps.numpy())
+    ref = _reference_fusibile(images, cams, ieee=ieee)
+    got = fusion.fuse_depth_maps(images.to(DEV), cams, carry_over=True, ieee=ieee).cpu().numpy()
+    assert len(ref) > 500
+    print(f"{shape} ieee={ieee}: reference {len(ref)} points, ours {len(got)}")
+    assert len(got) == len(ref), (len(got), len(ref))
+    exact = float((got == ref).all(axis=1).mean())
+    print(f"   max diff {np.abs(got - ref).max():.3e}; rows bit-identical {exact:.4%}")
+    assert np.array_equal(got, ref)
+    if w % 2 == 0 and (h * w) % 32 == 0:       # the zero-copy texture path samples identically
+        again = fusion.fuse_depth_maps(images.to(DEV), cams, carry_over=True, ieee=ieee, pitch_linear=True).cpu().numpy()
+        assert np.array_equal(again, got)

@@ -20,6 +20,7 @@ SIGNATURES = {
     "tmvs_peer_buffer_create": (c_int, [c_size_t, _P, _P]),
     "tmvs_peer_buffer_open": (c_int, [_P, _P]),
     "tmvs_peer_buffer_release": (c_int, [_P, c_int]),
+    "tmvs_peer_copy_async": (c_int, [_P, _P, c_size_t, _P]),
     "tmvs_error_string": (ctypes.c_char_p, [c_int]),
     "tmvs_packed_bytes": (c_size_t, [c_int] * 5),
     "tmvs_pack_sources": (c_int, [_P, c_int, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_uint, _P]),
@@ -38,7 +39,7 @@ SIGNATURES = {
     "tmvs_fusibile_fwd": (c_int, [_P, _P, c_int, c_int, c_int, ctypes.c_float, c_int, c_int, _P, ctypes.c_longlong, _P, _P,
                                   c_size_t, _P]),
     "tmvs_fusibile_workspace_bytes": (c_size_t, [c_int] * 3),
-    "tmvs_fusibile_tex_probe": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
+    "tmvs_fusibile_tex_probe": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     "tmvs_costvol_bwd": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P,
                                  c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P]),
     "tmvs_costvol_bwd_workspace_bytes": (c_size_t, [c_int] * 6 + [c_uint]),

@@ -111,13 +111,41 @@ class PeerMapSink:
         """[1, 2, H, W] view of slot `index` (peer memory on every rank but `dst`)."""
         return self.buffer[index:index + 1]
 
+    def push(self, index: int, depth: torch.Tensor, conf: torch.Tensor, stream: torch.cuda.Stream) -> None:
+        """Copy-engine transport: slot `index` <- (depth, conf) [1,H,W] each, as two asynchronous DMA copies on `stream`
+        (a side stream that has waited for the producing kernel).  No SM is involved and the producing kernel never
+        waits on the NVLink port; the tensors are kept alive for the stream (record_stream)."""
+        import ctypes
+        from . import _lib
+        slot = self.buffer[index]                        # [2,H,W] on rank dst
+        for k, t in enumerate((depth, conf)):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != slot[k].numel():
+                raise _lib.TmvsError("PeerMapSink.push: maps must be contiguous fp32 [1,H,W]")
+            t.record_stream(stream)
+            with torch.cuda.device(self.device):
+                rc = self._lib.tmvs_peer_copy_async(ctypes.c_void_p(slot[k].data_ptr()), ctypes.c_void_p(t.data_ptr()),
+                                                    t.numel() * 4, ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "tmvs_peer_copy_async")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001 -- interpreter shutdown: the driver reclaims the mapping
+            pass
+
     def result(self) -> Optional[torch.Tensor]:
         """The whole buffer on rank `dst`, None elsewhere (read it after a barrier that follows every writer's
         stream synchronisation)."""
         return self.buffer if self._owner else None
 
     def close(self) -> None:
-        if self._ptr.value:
+        if getattr(self, "_ptr", None) is not None and self._ptr.value:
             self.buffer = None
             self._lib.tmvs_peer_buffer_release(self._ptr, int(self._owner))
             self._ptr.value = 0
