@@ -201,7 +201,7 @@ def run_reference_arm(args, workload):
         "impl": "reference", "metric": "cost_volume_voxel_views_per_s", "value": value, "unit": "voxel-views/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(workload, vv, args.gpus, os.environ.get("TMVS_GATHER", "copy")),
+        "config": make_config(workload, vv, args.gpus, os.environ.get("TMVS_GATHER", "peer")),
         "cpu_baseline": {"value": value, "unit": "voxel-views/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxel-views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -334,9 +334,10 @@ def run_tmvs_arm(args, workload):
     # Multi-GPU: the stage-3 depth + confidence maps of every view end up on rank 0.  Default transport: the read-out
     # kernel writes them straight into rank 0's buffer through NVLink peer memory (sharding.PeerMapSink) -- no
     # collective, no extra kernel.  TMVS_GATHER=nccl keeps the NCCL all_gather on a side stream instead.
-    # TMVS_GATHER: "copy" (default) = the maps are pushed into rank 0's peer-mapped buffer by the DMA engines on a side
-    # stream; "peer" = the read-out kernel stores them there itself (round 1's default); "nccl" = all_gather.
-    gather = os.environ.get("TMVS_GATHER", "copy")
+    # TMVS_GATHER: "peer" (default) = the read-out kernel stores the maps into rank 0's peer-mapped buffer itself;
+    # "copy" = they are pushed there by the DMA engines on a side stream (measured slower at 8 GPUs: 2.175 vs 1.806 ms
+    # per view, profiles/r2_n8_gather_transports.json); "nccl" = all_gather on a side stream.
+    gather = os.environ.get("TMVS_GATHER", "peer")
     use_peer = world > 1 and workload["batch"] == 1 and gather in ("peer", "copy")
     comm = torch.cuda.Stream() if world > 1 else None
     sink = None

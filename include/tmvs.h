@@ -70,6 +70,9 @@ typedef void *tmvs_stream_t;
 #define TMVS_F_PACK_LDG        0x10u  /* tmvs_pack_sources: register-transpose kernel instead of the TMA engine */
 #define TMVS_F_FWD_SPLIT       0x20u  /* tmvs_costvol_fwd, C = 32: two channel passes of 16 (64 registers, 4 CTAs per SM) instead of
                                          one pass over all 32 (128 registers, 2 CTAs per SM); measured slower */
+#define TMVS_F_FWD_SWEEP       0x40u  /* tmvs_costvol_fwd (aggregated output, C = 8 or 16): epipolar-sweep kernel
+                                         (tmvs_costvol_sweep.cu) -- bit-identical results, fewer loads where the
+                                         hypotheses of a pixel are less than a pixel apart in the source image */
 #define TMVS_F_TABLE_MB(mb)    ((unsigned)(mb) << 16)   /* tmvs_costvol_bwd(+_workspace_bytes): cap of the cell-table
                                          workspace in MiB (0 = default 3072), e.g. to exercise the multi-pass path */
 

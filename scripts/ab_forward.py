@@ -11,13 +11,13 @@ from transmvsnet_b200 import _lib, ops, pipeline, synthetic  # noqa: E402
 
 dev = torch.device("cuda:0")
 rows = []
-variants = {"default": 0, "split": _lib.F_FWD_SPLIT}
+variants = {"default": 0, "split": _lib.F_FWD_SPLIT, "sweep": _lib.F_FWD_SWEEP}
 for stage in (1, 2, 3):
     st = synthetic.make_stage(stage, batch=1, n_views=5, height=1152, width=1600, seed=0)
     d = pipeline.stage_to_device(st, dev)
     packed = ops.pack_sources(d["features"][1:])
     for name, bits in variants.items():
-        if stage != 1 and name != "default":
+        if (stage != 1 and name == "split") or (stage == 1 and name == "sweep"):
             continue
         for want_views in ((False, True) if stage == 1 else (False,)):
             def run():

@@ -144,3 +144,39 @@ def test_channel_pass_kernel_agrees_with_the_one_pass_kernel():
                 agg_s, views_s = tm.cost_volume(*args, want_views=True)
             for a, b in ((agg_s, agg_1), (views_s, views_1)):
                 assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
+
+
+def test_epipolar_sweep_kernel_is_bit_identical_to_the_four_tap_kernel():
+    """TMVS_F_FWD_SWEEP re-indexes the plane loop by the source columns the epipolar walk crosses and reuses the channel
+    dot products of a source pixel between the planes whose footprints share it.  Same positions, same dots, same blend:
+    the aggregated volume must be BIT-identical to costvol_fwd_kernel's -- on cascade shapes (x- and y-major walks, both
+    directions: the four source cameras sit around the reference), ragged sizes and the image rim, per-plane [B,D]
+    hypotheses, a long-step stage-1 shape (warps fall back to the generic path), exaggerated geometry (walks that jump,
+    turn steep or leave the image), and hypotheses that run backwards."""
+    from transmvsnet_b200 import _lib
+    cases = []
+    for stage, hw, batch, nv in ((2, (144, 200), 2, 5), (3, (96, 136), 1, 5), (2, (74, 106), 1, 4), (3, (40, 72), 2, 7),
+                                 (3, (8, 8), 1, 3)):
+        st = synthetic.make_stage(stage, batch=batch, n_views=nv, height=hw[0], width=hw[1], seed=61)
+        cases.append((st, geometry.stage_rot_trans(st.proj_matrix), st.depth_values))
+    st = synthetic.make_stage(2, batch=1, n_views=5, height=128, width=192, seed=62)
+    cases.append((st, geometry.stage_rot_trans(st.proj_matrix), st.depth_values[:, :, 0, 0].contiguous()))      # [B,D]
+    cases.append((st, geometry.stage_rot_trans(st.proj_matrix), st.depth_values.flip(1).contiguous()))          # far -> near
+    rt = geometry.stage_rot_trans(st.proj_matrix).clone()
+    rt[:, :, 0:6] *= 3.0                                                                                          # 3x zoom: jumps
+    rt[:, :, 9:11] *= 3.0
+    cases.append((st, rt, st.depth_values))
+    rt = geometry.stage_rot_trans(st.proj_matrix).clone()
+    rt[:, :, 9] += 40.0                                                                                           # pushed off the image
+    rt[:, :, 11] -= 300.0                                                                                         # some z < 1e-6
+    cases.append((st, rt, st.depth_values))
+    st16 = synthetic.make_stage(1, batch=1, n_views=4, height=128, width=160, channels=16, num_depth=24, seed=63)
+    cases.append((st16, geometry.stage_rot_trans(st16.proj_matrix), st16.depth_values))                          # ~2 px per plane
+    for st, rt, dv in cases:
+        feats = [cu(f) for f in st.features]
+        packed = ops.pack_sources(feats[1:])
+        for arith in ("cuda", "cpu"):
+            want, _ = ops.cost_volume_packed(feats[0], packed, rt, cu(dv), cu(st.view_weights), False, True, arith=arith)
+            with ops.extra_flags(_lib.F_FWD_SWEEP):
+                got, _ = ops.cost_volume_packed(feats[0], packed, rt, cu(dv), cu(st.view_weights), False, True, arith=arith)
+            assert torch.equal(got, want), (st.stage, tuple(dv.shape), arith, float((got - want).abs().max()))

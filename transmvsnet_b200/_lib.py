@@ -56,6 +56,7 @@ F_FWD_TMA = 0x4
 F_BWD_SCAN = 0x8
 F_PACK_LDG = 0x10
 F_FWD_SPLIT = 0x20
+F_FWD_SWEEP = 0x40
 
 
 def f_table_mb(mb: int) -> int:

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libtmvs_sm100a.so")
-SOURCES = ["tmvs_pack.cu", "tmvs_pack_tma.cu", "tmvs_costvol.cu", "tmvs_costvol_tma.cu", "tmvs_costvol_bwd.cu", "tmvs_costvol_bwd_cells.cu", "tmvs_readout.cu", "tmvs_fusion.cu"]
+SOURCES = ["tmvs_pack.cu", "tmvs_pack_tma.cu", "tmvs_costvol.cu", "tmvs_costvol_sweep.cu", "tmvs_costvol_tma.cu", "tmvs_costvol_bwd.cu", "tmvs_costvol_bwd_cells.cu", "tmvs_readout.cu", "tmvs_fusion.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -20,6 +20,12 @@ int tmvs_costvol_fwd_tma(const float *ref, int64_t rB, int64_t rC, int64_t rH, i
                          float *sim_views, float *agg, int B, int C, int D, int H, int W, int n_src, unsigned flags,
                          cudaStream_t st);
 
+// epipolar-sweep variant (tmvs_costvol_sweep.cu); TMVS_E_UNSUPPORTED when it does not apply
+int tmvs_costvol_fwd_sweep(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64_t rW, const float *depth,
+                           int per_pixel, const float *vw, int vw_shift, int vw_w, int vw_hw, float *agg, int b_total,
+                           int b_first, int bc, int C, int D, int H, int W, int n_src, bool recip, const TmvsFwdConst &kc,
+                           const TmvsGeom &geom, cudaStream_t st);
+
 namespace {
 
 // Tunables (defaults = the values picked by scripts/tune_costvol.py on a B200, see profiles/README.md)
@@ -483,6 +489,12 @@ int costvol_fwd_impl(const float *ref, int64_t rB, int64_t rC, int64_t rH, int64
         for (int i = 0; i < TMVS_MAX_SRC_VIEWS; ++i) geom.img[i] = i < n_src ? (const float4 *)views[i] : nullptr;
         dim3 grid(((W + kTileX - 1) / kTileX) * n_dchunks, (H + kTileY - 1) / kTileY, bc);
         int rc;
+        if ((flags & TMVS_F_FWD_SWEEP) && agg && !sim_views) {
+            rc = tmvs_costvol_fwd_sweep(ref, rB, rC, rH, rW, depth, per_pixel, view_weights, vw_shift, vw_w, vw_hw, agg, B, b0,
+                                        bc, C, D, H, W, n_src, recip, kc, geom, st);
+            if (rc == TMVS_OK) continue;
+            if (rc != TMVS_E_UNSUPPORTED) return rc;
+        }
 #define TMVS_FWD_ARGS c4, (flags & TMVS_F_FWD_SPLIT) != 0, sim_views != nullptr, agg != nullptr, grid, block, st, ref, rB, rC, rH, rW,                   \
                       depth, view_weights, vw_shift, vw_w, vw_hw, sim_views, agg, B, b0, bc, C, c4, D, H, W, n_src,       \
                       n_dchunks, kc, geom
