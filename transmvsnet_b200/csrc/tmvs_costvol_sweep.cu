@@ -15,6 +15,14 @@
 // per plane along the major axis) instead of 4 * C4: 2.5-2.9 instead of 4 (x C4) on the config-2 geometry
 // (scripts/sim_l1_banks.py).
 //
+// MEASURED (B200, config 2, profiles/r2_sweep_ncu_v3.csv, r2_ab_forward_sweep.json): the loads do drop -- stage 2: 23.8 M
+// global load requests instead of 32.0 M (-26 %), 139.9 M L1 wavefronts instead of 179.5 M (-22 %); stage 3 (D = 8): -8 % /
+// -3 % -- but the re-indexed loop costs instructions (stage 2: 483 M warp instructions instead of 314 M, 25.5 instead of
+// 31.7 active lanes per instruction; 80 registers instead of 64) and the kernel turns from pipe-bound (91 % of the L1 data
+// pipe, 41 % issue) into issue/latency-bound (59 % pipe, 54 % issue): 0.820 ms instead of 0.683 ms at stage 2, 0.621
+// instead of 0.392 ms at stage 3.  Hence OPT-IN (TMVS_F_FWD_SWEEP), not the default; kept because it is exact and wins
+// on load traffic, i.e. it is the starting point wherever hypotheses are denser than ~0.5 px per plane.
+//
 // Always exact: a plane whose footprint is not wholly inside the image, not on the current column pair, or not inside
 // the three-pixel windows (walks steeper than 1:2, walks that jump or turn back, z < 1e-6 ...) takes the generic four-tap
 // path inline.  A warp whose lanes disagree about the walk (major axis, direction) or whose hypothesis step is long
@@ -144,52 +152,66 @@ __device__ __forceinline__ Window load_window(const float4 *img, int c, int base
 
 // One view of one thread's planes through the sweep.  SGN = +1: the walk moves towards larger major coordinates,
 // -1: towards smaller ones.  emit(k, s) receives the per-view similarity sum (before the 1/C of the channel mean).
+//
+// The loop is WARP-SYNCHRONOUS: every iteration all lanes that still have planes advance their windows by exactly one
+// column -- one window load executed by the whole warp -- and then emit the 0..2 planes that sit on the new column pair.
+// A lane whose next plane is two columns ahead simply emits nothing for one iteration; only a gap of three or more
+// columns (clamped or invalid positions) re-anchors, as a divergent extra load.  (A first version let each lane jump
+// ahead on its own: with per-pixel hypotheses some lane of nearly every warp did, and the extra partial-warp loads
+// cost more requests than the reuse saved -- profiles/r2_sweep_ncu_v1.csv.)
 template <int C4T, bool XMAJOR, bool RECIP, bool PER_PIXEL, typename Emit>
 __device__ __forceinline__ void sweep_view(const float4 *img, const float2 (&r)[2 * C4T], const TmvsFwdConst &kc,
                                            float rx, float ry, float rz, float tx, float ty, float tz,
-                                           const float *dep_base, int dep_stride, int nd, int sgn, int minor_up, Emit emit)
+                                           const float *dep_base, int dep_stride, int nd, int sgn, int minor_up,
+                                           unsigned lanes, Emit emit)
 {
+    const bool fwd = sgn > 0;
     int k = 0;
     Plane p = make_plane<RECIP>(rx, ry, rz, tx, ty, tz, __ldg(dep_base), kc);
     // mirrored major coordinate: g grows along the walk; the footprint of a plane sits on columns (g, g + 1)
-    auto g_of = [&](const Plane &q) { const int fu = XMAJOR ? q.x0 : q.y0; return sgn > 0 ? fu : -(fu + 1); };
-    auto col_of = [&](int g) { return sgn > 0 ? g : -g; };
+    auto g_of = [&](const Plane &q) { const int fu = XMAJOR ? q.x0 : q.y0; return fwd ? fu : -(fu + 1); };
+    auto col_of = [&](int g) { return fwd ? g : -g; };
     auto base_of = [&](const Plane &q) { const int fv = XMAJOR ? q.y0 : q.x0; return minor_up ? fv : fv - 1; };
-    int gA = g_of(p);
-    Window A = load_window<C4T, XMAJOR>(img, col_of(gA), base_of(p), r, kc);
-    Window B = load_window<C4T, XMAJOR>(img, col_of(gA + 1), base_of(p), r, kc);
-    for (;;) {
-        while (k < nd) {
-            const int gk = g_of(p);
-            if (gk > gA) break;                                        // this plane needs later columns
-            const int fv = XMAJOR ? p.y0 : p.x0;
-            // lo = the window on major coordinate fu, hi = the one on fu + 1
-            const Window &lo = sgn > 0 ? A : B, &hi = sgn > 0 ? B : A;
-            const unsigned il = (unsigned)(fv - lo.base), ih = (unsigned)(fv - hi.base);
-            const bool interior = (unsigned)p.x0 < (unsigned)kc.wm1 && (unsigned)p.y0 < (unsigned)kc.hm1;
-            float s;
-            if (gk == gA && interior && il <= 1u && ih <= 1u) {
-                const float l0 = il ? lo.t1 : lo.t0, l1 = il ? lo.t2 : lo.t1;
-                const float h0 = ih ? hi.t1 : hi.t0, h1 = ih ? hi.t2 : hi.t1;
-                // taps (x0,y0), (x0+1,y0), (x0,y0+1), (x0+1,y0+1)
-                s = XMAJOR ? blend4(p, l0, h0, l1, h1) : blend4(p, l0, l1, h0, h1);
-            } else {
-                s = plane_generic<C4T>(img, p, r, kc);
+    int gA = g_of(p) - 1;                       // the first iteration shifts onto the first plane's column
+    Window A, B = load_window<C4T, XMAJOR>(img, col_of(gA + 1), base_of(p), r, kc);
+    A = B;
+    while (__any_sync(lanes, k < nd)) {
+        if (k < nd) {
+            // ---- advance by one column (whole warp), or re-anchor across a gap
+            const int gap = g_of(p) - gA;
+            if (gap >= 3 || gap < 0) {
+                gA = g_of(p);
+                A = load_window<C4T, XMAJOR>(img, col_of(gA), base_of(p), r, kc);
+            } else if (gap >= 1) {
+                A = B;
+                ++gA;
             }
-            emit(k, s);
-            ++k;
-            if (k < nd) p = make_plane<RECIP>(rx, ry, rz, tx, ty, tz, __ldg(dep_base + (size_t)k * dep_stride), kc);
+            if (gap != 0) B = load_window<C4T, XMAJOR>(img, col_of(gA + 1), base_of(p), r, kc);
+            // ---- the planes on this column pair (usually one, sometimes none or two)
+#pragma unroll 1
+            while (k < nd && g_of(p) == gA) {
+                const int fv = XMAJOR ? p.y0 : p.x0;
+                // lo = the window on major coordinate fu, hi = the one on fu + 1 (selected by value: a reference to one
+                // of two locals would force both windows into local memory, i.e. back onto the load pipe)
+                const int lo_base = fwd ? A.base : B.base, hi_base = fwd ? B.base : A.base;
+                const unsigned il = (unsigned)(fv - lo_base), ih = (unsigned)(fv - hi_base);
+                const bool interior = (unsigned)p.x0 < (unsigned)kc.wm1 && (unsigned)p.y0 < (unsigned)kc.hm1;
+                float s;
+                if (interior && il <= 1u && ih <= 1u) {
+                    const float lo0 = fwd ? A.t0 : B.t0, lo1 = fwd ? A.t1 : B.t1, lo2 = fwd ? A.t2 : B.t2;
+                    const float hi0 = fwd ? B.t0 : A.t0, hi1 = fwd ? B.t1 : A.t1, hi2 = fwd ? B.t2 : A.t2;
+                    const float l0 = il ? lo1 : lo0, l1 = il ? lo2 : lo1;
+                    const float h0 = ih ? hi1 : hi0, h1 = ih ? hi2 : hi1;
+                    // taps (x0,y0), (x0+1,y0), (x0,y0+1), (x0+1,y0+1)
+                    s = XMAJOR ? blend4(p, l0, h0, l1, h1) : blend4(p, l0, l1, h0, h1);
+                } else {
+                    s = plane_generic<C4T>(img, p, r, kc);
+                }
+                emit(k, s);
+                ++k;
+                if (k < nd) p = make_plane<RECIP>(rx, ry, rz, tx, ty, tz, __ldg(dep_base + (size_t)k * dep_stride), kc);
+            }
         }
-        if (k >= nd) break;
-        const int gk = g_of(p);
-        if (gk == gA + 1) {                                            // next column: the newer window becomes the older
-            A = B;
-            gA = gk;
-        } else {                                                       // the walk jumped: re-anchor
-            gA = gk;
-            A = load_window<C4T, XMAJOR>(img, col_of(gA), base_of(p), r, kc);
-        }
-        B = load_window<C4T, XMAJOR>(img, col_of(gA + 1), base_of(p), r, kc);
     }
 }
 
@@ -254,7 +276,7 @@ costvol_fwd_sweep_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, 
         const bool xmajor = fabsf(dx) >= fabsf(dy);
         const float dM = xmajor ? dx : dy, dm = xmajor ? dy : dx;
         const int sgn = dM >= 0.0f ? 1 : -1;
-        const int minor_up = (dm >= 0.0f) == (dM >= 0.0f);          // along the walk the minor coordinate grows
+        const int minor_up = dm >= 0.0f;                            // in plane order the minor coordinate grows
         // worth sweeping: at most ~1.2 columns per plane, and a walk no steeper than ~1:2 (three-pixel windows)
         const bool fits = fabsf(dM) <= 1.2f * (float)nd + 1.0f && fabsf(dm) <= 0.5f * fabsf(dM) + 1.0f;
         const bool uniform = __all_sync(lanes, fits) &&
@@ -264,10 +286,10 @@ costvol_fwd_sweep_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, 
         if (uniform) {
             if (xmajor)
                 sweep_view<C4T, true, RECIP, PER_PIXEL>(img, r, kc, ray.rx, ray.ry, ray.rz, tx, ty, tz, dep_base, dep_stride,
-                                                        nd, sgn, minor_up, emit);
+                                                        nd, sgn, minor_up, lanes, emit);
             else
                 sweep_view<C4T, false, RECIP, PER_PIXEL>(img, r, kc, ray.rx, ray.ry, ray.rz, tx, ty, tz, dep_base, dep_stride,
-                                                         nd, sgn, minor_up, emit);
+                                                         nd, sgn, minor_up, lanes, emit);
         } else {
             const float *dep_p = dep_base;
             for (int k = 0; k < nd; ++k, dep_p += dep_stride)
