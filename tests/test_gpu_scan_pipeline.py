@@ -127,6 +127,21 @@ def test_process_scan_equals_the_per_view_cascade():
     pyr = sum(m.numel() * 4 for m in scan.pyramids[0])
     per_job = sum((st.logits.numel() + st.cur_depth.numel()) * 4 for st in scan.jobs[0]) + scan.jobs[0][0].view_weights.numel() * 4
     assert pipe.h2d_bytes == 7 * (pyr + per_job)
+    # the same scan captured as CUDA graphs (one per job, uploads of the next job forked beside the kernels) and
+    # replayed twice: identical maps, identical byte count
+    eager = [[{k: v.clone() for k, v in stage.items()} for stage in job] for job in res]
+    for rep in range(2):
+        for job in res:
+            for stage in job:
+                for v in stage.values():
+                    v.zero_()
+        res_g = pipe.process_scan(pinned, graphs=True)
+        torch.cuda.synchronize()
+        for j in range(len(scan.jobs)):
+            for s in range(3):
+                for k in ("depth", "photo_confidence"):
+                    assert torch.equal(res_g[j][s][k], eager[j][s][k]), (rep, j, s, k)
+        assert pipe.h2d_bytes == 7 * (pyr + per_job)
 
 
 def test_channel_pass_kernel_agrees_with_the_one_pass_kernel():
@@ -180,3 +195,50 @@ def test_epipolar_sweep_kernel_is_bit_identical_to_the_four_tap_kernel():
             with ops.extra_flags(_lib.F_FWD_SWEEP):
                 got, _ = ops.cost_volume_packed(feats[0], packed, rt, cu(dv), cu(st.view_weights), False, True, arith=arith)
             assert torch.equal(got, want), (st.stage, tuple(dv.shape), arith, float((got - want).abs().max()))
+
+
+def test_process_scan_with_the_regulariser_on_the_device():
+    """cost_regularization given as callables (the reference's DepthNet.forward argument): logits are produced on the
+    device from the aggregated similarity, nothing but features, seeds and stage-1 weights crosses PCIe."""
+    scan = synthetic.make_scan(5, n_views=4, height=64, width=96, seed=43, lean=False)
+    pinned = pipeline.pin_scan(scan)
+    pipe = pipeline.HostPipeline(DEV)
+    gain = [lambda x: x * 25.0] * 3
+    res = pipe.process_scan(pinned, cost_regularization=gain)
+    torch.cuda.synchronize()
+    for j, job in enumerate(scan.jobs):
+        for s, st in enumerate(job):
+            dev = pipeline.stage_to_device(st, DEV)
+            dv = ops.depth_hypotheses(cu(st.cur_depth), st.num_depth, st.interval_pixel, st.image_hw, st.image_hw[0] // st.bdhw[2])
+            packed = ops.pack_sources(dev["features"][1:])
+            sim, _ = ops.cost_volume_packed(dev["features"][0], packed, dev["rot_trans"], dv, dev["view_weights"], False, True)
+            _, _, depth, conf = ops.softmax_wta(sim * 25.0, dv)
+            assert torch.equal(res[j][s]["depth"], depth.cpu()) and torch.equal(res[j][s]["photo_confidence"], conf.cpu())
+    pyr = sum(m.numel() * 4 for m in scan.pyramids[0])
+    per_job = sum(st.cur_depth.numel() * 4 for st in scan.jobs[0]) + scan.jobs[0][0].view_weights.numel() * 4
+    assert pipe.h2d_bytes == 5 * (pyr + per_job)
+
+
+def test_backward_full_size_against_the_references_cuda_autograd():
+    """Config-2 stage 3 at full size (1152 x 1600, N = 5): grad_ref / grad_src of the fused path against the reference's
+    own op sequence differentiated by autograd on the same GPU (ATen grid_sampler_2d_backward: float atomics, so the
+    comparison is a tolerance, 1e-4, not bit equality) -- and ours twice, bit for bit."""
+    from conftest import assert_costvol_close
+    from oracle import torch_port
+    st = synthetic.make_stage(3, batch=1, n_views=5, height=1152, width=1600, seed=0)
+    feats = [cu(f) for f in st.features]
+    pm, dv, vw = cu(st.proj_matrix), cu(st.depth_values), cu(st.view_weights)
+    g = torch.randn(dv.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11))
+    fs = [f.clone().requires_grad_(True) for f in feats]
+    agg, _ = torch_port.cost_volume(fs, pm, dv, vw)
+    want = torch.autograd.grad(agg.squeeze(1), fs, g)
+    del agg
+    rt = geometry.stage_rot_trans(pm)                      # on the device: read in place by the kernels
+    runs = []
+    for _ in range(2):
+        fs2 = [f.clone().requires_grad_(True) for f in feats]
+        agg2, _ = tm.cost_volume(fs2[0], fs2[1:], rt, dv, vw)
+        runs.append(torch.autograd.grad(agg2, fs2, g))
+    for v, (a, b, w) in enumerate(zip(runs[0], runs[1], want)):
+        assert torch.equal(a, b), f"view {v}: backward is not bit-reproducible"
+        assert_costvol_close(a.cpu().numpy(), w.cpu().numpy(), f"full-size stage 3 grad of view {v}")
