@@ -1,45 +1,62 @@
-"""Rebuild tmvs_costvol_bwd.cu / tmvs_costvol_bwd_cells.cu with different tunables and time grad_src at the DTU stage sizes (GPU box)."""
-import ctypes, json, os, subprocess, sys
+"""Build variants of the backward kernels (occupancy tunables) HERE (nvcc cross-compiles without a GPU) into
+build/variants/, then time each on the GPU box:
+   python scripts/tune_bwd.py build        # in the build container
+   python scripts/tune_bwd.py time [dtu|bld]     # on the GPU box (the variant libraries travel with the snapshot)"""
+import json
+import os
+import subprocess
+import sys
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-import torch
-from transmvsnet_b200 import _lib, build, geometry, ops, synthetic
-CSRC = os.path.join(REPO, "transmvsnet_b200", "csrc")
-SCRATCH = os.path.join(REPO, "gpurun_out", "tune")
-os.makedirs(SCRATCH, exist_ok=True)
-dev = torch.device("cuda:0")
-flags0 = [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-objs = {}
-for src in build.SOURCES:
-    if src not in ("tmvs_costvol_bwd.cu", "tmvs_costvol_bwd_cells.cu"):
-        o = os.path.join(SCRATCH, src + ".o")
-        subprocess.run(["nvcc", *flags0, "-c", os.path.join(CSRC, src), "-o", o], check=True, capture_output=True)
-        objs[src] = o
-cases = []
-for stage in (1, 2, 3):
-    st = synthetic.make_stage(stage, batch=1, n_views=5, height=1152, width=1600, seed=0)
-    rt = geometry.stage_rot_trans(st.proj_matrix)
-    cases.append((st, rt))
-for defs in json.loads(sys.argv[1]):
-    o = os.path.join(SCRATCH, "bwd.o")
-    o2 = os.path.join(SCRATCH, "bwd_cells.o")
-    r = subprocess.run(["nvcc", *flags0, *[f"-D{k}={v}" for k, v in defs.items()], "-c", os.path.join(CSRC, "tmvs_costvol_bwd.cu"), "-o", o], capture_output=True, text=True)
-    r2 = subprocess.run(["nvcc", *flags0, *[f"-D{k}={v}" for k, v in defs.items()], "-c", os.path.join(CSRC, "tmvs_costvol_bwd_cells.cu"), "-o", o2], capture_output=True, text=True)
-    if r.returncode or r2.returncode:
-        print(defs, "build failed", r.stderr[-200:], r2.stderr[-200:]); continue
-    lib = os.path.join(SCRATCH, "lib.so")
-    subprocess.run(["nvcc", "-shared", "-o", lib, *objs.values(), o, o2, "-gencode", "arch=compute_100a,code=sm_100a"], check=True)
-    import shutil; lib2 = os.path.join(SCRATCH, f"lib_{abs(hash(str(defs)))}.so"); shutil.copy(lib, lib2)
-    L = ctypes.CDLL(lib2)
-    for name, (res, args) in _lib.SIGNATURES.items():
-        fn = getattr(L, name); fn.restype, fn.argtypes = res, args
-    _lib._LIB = L
-    out = []
-    for st, rt in cases:
-        feats = [f.to(dev) for f in st.features]; dv = st.depth_values.to(dev)
-        packed = ops.pack_sources(feats[1:]); gv = torch.randn(4, *dv.shape, device=dev)
-        f = lambda: ops.costvol_backward_packed(feats[0], packed, rt, dv, gv, False, True)
-        f(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); f(); f(); e1.record(); torch.cuda.synchronize()
-        out.append(round(e0.elapsed_time(e1) / 2, 3))
-    print(defs, out, flush=True)
+from transmvsnet_b200 import build  # noqa: E402
+
+OUT = os.path.join(REPO, "build", "variants")
+VARIANTS = {
+    "base": {},
+    "gather244": {"TMVS_GATHER_MINB4": 4, "TMVS_GATHER_MINB2": 4},
+    "gather245_ref245": {"TMVS_GATHER_MINB4": 4, "TMVS_GATHER_MINB2": 5, "TMVS_BWDREF_MINB4": 4, "TMVS_BWDREF_MINB2": 5},
+    "ref222": {"TMVS_BWDREF_MINB4": 2, "TMVS_BWDREF_MINB2": 2},
+}
+
+
+def build_all():
+    os.makedirs(OUT, exist_ok=True)
+    flags = [f for f in build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    for tag, defs in VARIANTS.items():
+        objs = []
+        for src in build.SOURCES:
+            tuned = src in ("tmvs_costvol_bwd.cu", "tmvs_costvol_bwd_cells.cu")
+            obj = os.path.join(OUT, f"{tag if tuned else 'common'}_{src}.o")
+            if tuned or not os.path.exists(obj):
+                d = [f"-D{k}={v}" for k, v in defs.items()] if tuned else []
+                subprocess.run(["nvcc", *flags, *d, "-c", os.path.join(build.CSRC, src), "-o", obj], check=True)
+            objs.append(obj)
+        subprocess.run(["nvcc", "-shared", "-o", os.path.join(OUT, f"libtmvs_{tag}.so"), *objs, "-gencode",
+                        "arch=compute_100a,code=sm_100a"], check=True)
+        print("built", tag, flush=True)
+
+
+def time_all(which):
+    rows = []
+    for tag in VARIANTS:
+        lib = os.path.join(OUT, f"libtmvs_{tag}.so")
+        if not os.path.exists(lib):
+            continue
+        res = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "time_bwd.py"), which],
+                             env=dict(os.environ, TMVS_LIB_PATH=lib), capture_output=True, text=True)
+        line = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-300:]
+        print(tag, line, flush=True)
+        try:
+            rows.append({"variant": tag, "defs": VARIANTS[tag], **json.loads(line)})
+        except ValueError:
+            pass
+    os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(REPO, "gpurun_out", f"tune_bwd_{which}.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "build":
+        build_all()
+    else:
+        time_all(sys.argv[2] if len(sys.argv) > 2 else "dtu")

@@ -41,8 +41,20 @@ constexpr int kCellW = kTX + 1, kCellH = kTY + 1, kCells = kCellW * kCellH;
 constexpr int kEmpty = 0x7fffffff;
 
 // --------------------------------------------------------------------------------------------- grad_ref
+// resident CTAs per SM (registers): the gather is a chain of dependent L1 loads, so occupancy is what hides its latency
+#ifndef TMVS_BWDREF_MINB8
+#define TMVS_BWDREF_MINB8 2
+#endif
+#ifndef TMVS_BWDREF_MINB4
+#define TMVS_BWDREF_MINB4 4
+#endif
+#ifndef TMVS_BWDREF_MINB2
+#define TMVS_BWDREF_MINB2 4
+#endif
+template <int C4T> struct BwdRefMinBlocks { static constexpr int value = C4T >= 8 ? TMVS_BWDREF_MINB8 : (C4T >= 4 ? TMVS_BWDREF_MINB4 : TMVS_BWDREF_MINB2); };
+
 template <int C4T, bool EXACT, bool PER_PIXEL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BwdRefMinBlocks<C4T>::value)
 bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ depth, const float *__restrict__ G,
                float *__restrict__ partial, int b_total, int b_first, int b_chunk, int C, int c4, int D, int H, int W,
                const __grid_constant__ TmvsGeom geom)
