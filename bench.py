@@ -50,6 +50,9 @@ WORKLOADS = {
     # configs[3] forward part: BlendedMVS-shaped 768x576, N=7, batch 8
     "bld": dict(height=576, width=768, n_views=7, kind="unit", batch=8,
                 name="BlendedMVS-shaped 576x768 N=7 B=8 D=48/32/8 fp32 forward"),
+    # seconds on a CPU: exercises both arms' plumbing in the test suite, never a reported number
+    "tiny": dict(height=64, width=96, n_views=3, kind="dtu", batch=1,
+                 name="tiny 64x96 N=3 D=48/32/8 (plumbing test only)"),
 }
 SCAN_VIEWS = 49         # views per scan in the e2e figure (DTU: 49 per scan, datasets/general_eval.py:25-57)
 

@@ -242,3 +242,29 @@ def test_backward_full_size_against_the_references_cuda_autograd():
     for v, (a, b, w) in enumerate(zip(runs[0], runs[1], want)):
         assert torch.equal(a, b), f"view {v}: backward is not bit-reproducible"
         assert_costvol_close(a.cpu().numpy(), w.cpu().numpy(), f"full-size stage 3 grad of view {v}")
+
+
+def test_bench_line_on_a_tiny_workload():
+    """bench.py end to end on the GPU with a tiny workload: one JSON line carrying the contract's keys, an e2e figure
+    measured over a scan with declared copies, and a launch count that matches 9 launches per step."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", "tiny", "--steps", "4", "--warmup", "3",
+                          "--scan-views", "5", "--no-workloads", "--no-cpu-baseline"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-800:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                "data", "config", "gpu_launches", "roofline", "e2e", "clocks"):
+        assert key in line, key
+    assert line["gpu_launches"] == 9 * 4 and line["steps"] == 4 and line["n_gpus"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+    assert line["e2e"]["with_device_side_regulariser"]["h2d_bytes_per_step"] < line["e2e"]["h2d_bytes_per_step"]
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3

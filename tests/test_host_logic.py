@@ -143,3 +143,29 @@ def test_library_reads_no_environment_and_keeps_no_arithmetic_state():
         assert "getenv" not in text and "g_arith" not in text, path
     syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "tmvs_set_reference_arithmetic" not in syms and "tmvs_costvol_fwd_cached" in syms
+
+
+def test_bench_reference_arm_runs_the_staged_reference_and_prints_the_contract_line():
+    """bench.py --impl reference on the tiny workload (seconds on a CPU): ONE JSON line on stdout with the keys the driver
+    reads, timed through the reference's own DepthNet.forward when oracle/_ref is staged (kind "reference")."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    from oracle import build as oracle_build
+    oracle_build.build_ref()
+    res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-500:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    staged = oracle_build.import_reference() is not None
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["config"]["workload"].startswith("tiny") and "timed_sample" not in line["config"]
