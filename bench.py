@@ -536,7 +536,11 @@ def run_tmvs_arm(args, workload):
                            "is packed once per scan, then stays resident) + the stand-in 3-D CNN logits + stage-1 view "
                            "weights + depth seeds; hypotheses generated on the device",
                "d2h_bytes_per_step": pipeline.HostPipeline.d2h_bytes(scan.jobs[0]), "steps": k_e2e,
-               "ms_per_step": ms / k_e2e, "with_device_side_regulariser": device_reg,
+               "ms_per_step": ms / k_e2e,
+               # what the host link delivered, summed over the ranks (one rank alone: ~54 GB/s of PCIe; the 8-GPU box
+               # saturates near 165-180 GB/s in total, which is what bounds the end-to-end figure at 8 GPUs)
+               "h2d_gbps_all_ranks": round(world * h2d_host_logits / (ms / k_e2e * 1e-3) / 1e9, 1),
+               "with_device_side_regulariser": device_reg,
                "scan": f"{len(scan.pyramids)} views, every view the reference view once, {workload['n_views'] - 1} source "
                        f"views each (ring pairing), {n_scans} scan(s) timed after one warm-up scan; one scan per rank"}
         del scan, pipe
