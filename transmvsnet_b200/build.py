@@ -58,8 +58,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 # kernels whose full SASS is committed (the hot instantiations); every other kernel gets an opcode histogram
-HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1ELb0E", "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1ELb0E",
-               "costvol_fwd_kernelILi2ELb1ELb1ELb0ELb1ELb0E", "costvol_fwd_kernelILi8ELb1ELb1ELb1ELb0ELb0E",
+HOT_KERNELS = ("costvol_fwd_kernelILi8ELb1ELb1ELb0ELb1ELb1ELi1E", "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1ELb1ELi1E",
+               "costvol_fwd_kernelILi2ELb1ELb1ELb0ELb1ELb1ELi1E", "costvol_fwd_kernelILi8ELb1ELb1ELb1ELb0ELb1ELi1E",
+               "costvol_fwd_kernelILi4ELb1ELb1ELb0ELb1ELb1ELi2E", "costvol_fwd_sweep_kernelILi4ELi16ELb1ELb1E",
+               "costvol_fwd_sweep_kernelILi2ELi8ELb1ELb1E", "cells_gather_warp_kernelILi8E",
                "pack_sources_nchw4_kernel", "homo_warp_fwd_kernelILb1E", "softmax_wta_kernelILi48E",
                "softmax_wta_kernelILi32E", "softmax_wta_kernelILi8E", "depth_wta_kernel",
                "bwd_src_kernelILi8ELb1ELb1E", "bwd_ref_kernelILi8ELb1ELb1E", "bwd_bbox_kernelILb1E",
