@@ -374,6 +374,7 @@ cells_gather_warp_kernel(const float *__restrict__ gout, CellTables tb, float *_
 #pragma unroll
         for (int cls = 0; cls < 4; ++cls) {
             const unsigned cell = c0 - ((cls & 1) ? 1u : 0u) - ((cls & 2) ? wp1 : 0u);
+            TMVS_ASSERT(cell < ncell);
             const uint4 pr = __ldg(par_d + cell);
             unsigned *v = ids[cls];
             v[0] = pr.x; v[1] = pr.y; v[2] = pr.z; v[3] = pr.w; v[4] = kEmptyId; v[5] = kEmptyId;
@@ -401,6 +402,7 @@ cells_gather_warp_kernel(const float *__restrict__ gout, CellTables tb, float *_
                 if (id == kEmptyId) continue;
                 const unsigned px = id & 0xffffu, py = id >> 16;
                 const unsigned pix = py * (unsigned)W + px;
+                TMVS_ASSERT(px < (unsigned)W && py < (unsigned)H);
                 const float2 c = __ldg(pos_d + pix);
                 const float wx = (cls & 1) ? __fsub_rn(c.x, qxf - 1.0f) : __fsub_rn(qxf + 1.0f, c.x);
                 const float wy = (cls & 2) ? __fsub_rn(c.y, qyf - 1.0f) : __fsub_rn(qyf + 1.0f, c.y);

@@ -110,6 +110,7 @@ __device__ __forceinline__ float plane_generic(const float4 *img, Plane p, const
         const unsigned oa = (xa >> 3) * c4x8 + (xa & 7u), ob = (xb >> 3) * c4x8 + (xb & 7u);
         o00 = ra + oa; o01 = ra + ob; o10 = rb + oa; o11 = rb + ob;
     }
+    TMVS_ASSERT(max(max(o00, o01), max(o10, o11)) + (C4T - 1) * 8u < (unsigned)((kc.hm1 + 1) * kc.row));
     // the four channel dots interleaved per group, as in costvol_fwd_kernel (the sums are the same either way: each
     // chain only ever adds its own tap's products)
     return blend4(p, tap_dot<C4T>(img, o00, r), tap_dot<C4T>(img, o01, r), tap_dot<C4T>(img, o10, r),
@@ -136,6 +137,7 @@ __device__ __forceinline__ Window load_window(const float4 *img, int c, int base
         const unsigned ox = (xc >> 3) * c4x8 + (xc & 7u);
         const unsigned r0 = (unsigned)min(max(base, 0), kc.hm1), r1 = (unsigned)min(max(base + 1, 0), kc.hm1),
                        r2 = (unsigned)min(max(base + 2, 0), kc.hm1);
+        TMVS_ASSERT(r2 * (unsigned)kc.row + ox + (C4T - 1) * 8u < (unsigned)((kc.hm1 + 1) * kc.row));
         w.t0 = tap_dot<C4T>(img, r0 * (unsigned)kc.row + ox, r);
         w.t1 = tap_dot<C4T>(img, r1 * (unsigned)kc.row + ox, r);
         w.t2 = tap_dot<C4T>(img, r2 * (unsigned)kc.row + ox, r);
@@ -143,6 +145,7 @@ __device__ __forceinline__ Window load_window(const float4 *img, int c, int base
         const unsigned ro = (unsigned)min(max(c, 0), kc.hm1) * (unsigned)kc.row;
         const unsigned x0 = (unsigned)min(max(base, 0), kc.wm1), x1 = (unsigned)min(max(base + 1, 0), kc.wm1),
                        x2 = (unsigned)min(max(base + 2, 0), kc.wm1);
+        TMVS_ASSERT(ro + (x2 >> 3) * c4x8 + (x2 & 7u) + (C4T - 1) * 8u < (unsigned)((kc.hm1 + 1) * kc.row));
         w.t0 = tap_dot<C4T>(img, ro + (x0 >> 3) * c4x8 + (x0 & 7u), r);
         w.t1 = tap_dot<C4T>(img, ro + (x1 >> 3) * c4x8 + (x1 & 7u), r);
         w.t2 = tap_dot<C4T>(img, ro + (x2 >> 3) * c4x8 + (x2 & 7u), r);
