@@ -356,6 +356,11 @@ def run_tmvs_arm(args, workload):
         if float(ok.item()) == 0.0:
             sink, use_peer, gather = None, False, "nccl"
     step_no = [0]
+    copy_done = [None, None]
+    local_maps = None
+    if sink is not None and gather == "copy":
+        h3, w3 = host[-1].depth_values.shape[2:]
+        local_maps = [torch.zeros(1, 2, h3, w3, device=dev) for _ in range(2)]
 
     def step():
         if sink is not None:    # ring of two step-slots per rank: this step's maps land in slot (parity, rank)
@@ -363,11 +368,18 @@ def run_tmvs_arm(args, workload):
             step_no[0] += 1
             if gather == "peer":
                 return pipeline.run_cascade(dev_stages, out_maps=sink.slot(slot))
-            outs = pipeline.run_cascade(dev_stages)
+            # "copy": the read-out kernel writes a persistent LOCAL map pair (two sets, alternating), the DMA engines move
+            # it into rank 0's buffer on the side stream; set p is not rewritten before its previous copy has left
+            p = step_no[0] & 1
+            if copy_done[p] is not None:
+                torch.cuda.current_stream().wait_event(copy_done[p])
+            outs = pipeline.run_cascade(dev_stages, out_maps=local_maps[p])
             ready = torch.cuda.Event()
             ready.record()
             comm.wait_event(ready)
-            sink.push(slot, outs[-1]["depth"], outs[-1]["photo_confidence"], comm)
+            sink.push(slot, local_maps[p][:, 0], local_maps[p][:, 1], comm)
+            copy_done[p] = torch.cuda.Event()
+            copy_done[p].record(comm)
             return outs
         outs = pipeline.run_cascade(dev_stages)
         if world > 1:       # gather this view's stage-3 depth + confidence on rank 0, off the compute stream
@@ -406,7 +418,14 @@ def run_tmvs_arm(args, workload):
     sampler.active.clear()
     launches = _lib.LAUNCHES - launches0
     elapsed_ms = e0.elapsed_time(e1)
+    per_rank = None
     if world > 1:
+        # every rank's own device time and median SM clock: the max is the reported time; the spread shows how much of
+        # the distance to N x the 1-GPU figure is GPU-to-GPU variation rather than the gather
+        mine = torch.tensor([elapsed_ms / args.steps, float(statistics.median(sampler.sm)) if sampler.sm else 0.0], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(t[0]), 4) for t in allr], "sm_mhz": [float(t[1]) for t in allr]}
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
@@ -565,7 +584,7 @@ def run_tmvs_arm(args, workload):
             "ms_per_ref_view": elapsed_ms / args.steps / workload["batch"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(workload, vv, world, gather if use_peer else "nccl"),
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "workloads": extra,
+            "per_rank": per_rank, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "workloads": extra,
             "clocks": sampler.summary(),
         }
         emit(line)

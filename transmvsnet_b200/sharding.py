@@ -114,14 +114,14 @@ class PeerMapSink:
     def push(self, index: int, depth: torch.Tensor, conf: torch.Tensor, stream: torch.cuda.Stream) -> None:
         """Copy-engine transport: slot `index` <- (depth, conf) [1,H,W] each, as two asynchronous DMA copies on `stream`
         (a side stream that has waited for the producing kernel).  No SM is involved and the producing kernel never
-        waits on the NVLink port; the tensors are kept alive for the stream (record_stream)."""
+        waits on the NVLink port.  The caller keeps `depth` / `conf` alive and unmodified until the stream has passed the
+        copies (persistent buffers + an event, as bench.py does)."""
         import ctypes
         from . import _lib
         slot = self.buffer[index]                        # [2,H,W] on rank dst
         for k, t in enumerate((depth, conf)):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != slot[k].numel():
                 raise _lib.TmvsError("PeerMapSink.push: maps must be contiguous fp32 [1,H,W]")
-            t.record_stream(stream)
             with torch.cuda.device(self.device):
                 rc = self._lib.tmvs_peer_copy_async(ctypes.c_void_p(slot[k].data_ptr()), ctypes.c_void_p(t.data_ptr()),
                                                     t.numel() * 4, ctypes.c_void_p(stream.cuda_stream))
