@@ -338,7 +338,7 @@ def run_tmvs_arm(args, workload):
     # kernel writes them straight into rank 0's buffer through NVLink peer memory (sharding.PeerMapSink) -- no
     # collective, no extra kernel.  TMVS_GATHER=nccl keeps the NCCL all_gather on a side stream instead.
     # TMVS_GATHER: "peer" (default) = the read-out kernel stores the maps into rank 0's peer-mapped buffer itself;
-    # "copy" = they are pushed there by the DMA engines on a side stream (measured slower at 8 GPUs: 2.175 vs 1.806 ms
+    # "copy" = they are pushed there by the DMA engines on a side stream (the same time at 8 GPUs: 1.8064 vs 1.8063 ms
     # per view, profiles/r2_n8_gather_transports.json); "nccl" = all_gather on a side stream.
     gather = os.environ.get("TMVS_GATHER", "peer")
     use_peer = world > 1 and workload["batch"] == 1 and gather in ("peer", "copy")
