@@ -3,12 +3,13 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from transmvsnet_b200 import geometry, synthetic
-for devname in ("cpu", "cuda"):
+SIZES = [(1152, 1600), (576, 800), (288, 400), (264, 480), (144, 192)] if "--sizes" in sys.argv else [(1152, 1600)]
+for devname, (h, w) in [(d, hw) for d in ("cpu", "cuda") for hw in SIZES]:
     dev = torch.device(devname)
+    print(f"--- {devname} map {h}x{w}")
     st = synthetic.make_stage(3, batch=1, n_views=3, height=1152, width=1600, seed=0)
     rt = geometry.stage_rot_trans(st.proj_matrix.to(dev)).to(dev)
     rot = rt[0, :, :9].reshape(1, 3, 3)
-    h, w = 1152, 1600
     y, x = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev), torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
     xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(h * w, device=dev)))[None]
     ref = torch.matmul(rot, xyz)[0].double().cpu().numpy().astype(np.float32)          # [3,HW] fp32 bits

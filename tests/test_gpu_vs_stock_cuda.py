@@ -108,3 +108,37 @@ def test_forward_and_backward_beat_stock_pytorch_cuda():
     with open(os.path.join(out, "stock_cuda_timing.json"), "w") as f:
         json.dump({"config": "DTU 1152x1600 N=5, one reference view, fp32, B200", "rows": rows}, f, indent=1)
     print(json.dumps(rows))
+
+
+@pytest.mark.parametrize("shape", ["tnt", "bld"])
+def test_other_baseline_shapes_match_stock_cuda_at_full_size(shape):
+    """BASELINE configs 3 and 4 at their full sizes (T&T-shaped 1056x1920 N=7; BlendedMVS-shaped 576x768 N=7, two items
+    of the batch of 8): the fused forward against the reference's op sequence on the same GPU, default arithmetic,
+    <= 1e-4; for the BlendedMVS shape also the backward against the reference's autograd."""
+    from conftest import rel_err
+    cfg = {"tnt": dict(height=1056, width=1920, n_views=7, batch=1, kind="unit"),
+           "bld": dict(height=576, width=768, n_views=7, batch=2, kind="unit")}[shape]
+    for stage in (1, 2, 3):
+        st = synthetic.make_stage(stage, seed=3, **cfg)
+        dev = pipeline.stage_to_device(st, DEV)
+        feats, pm = dev["features"], st.proj_matrix.to(DEV)
+        rt = geometry.stage_rot_trans(pm)                       # device-resident, read in place
+        with torch.no_grad():
+            want, _ = torch_port.cost_volume(feats, pm, dev["depth_values"], dev["view_weights"])
+            got, _ = ops.cost_volume(feats[0], feats[1:], rt, dev["depth_values"], dev["view_weights"])
+        e_max, e_l2 = rel_err(got.cpu().numpy(), want.squeeze(1).cpu().numpy())
+        print(f"{shape} stage {stage}: forward max-rel {e_max:.2e} l2-rel {e_l2:.2e}")
+        assert e_max <= 1e-4 and e_l2 <= 1e-4, (shape, stage, e_max, e_l2)
+        if shape == "bld":
+            g = torch.randn(want.squeeze(1).shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+            fs = [f.clone().requires_grad_(True) for f in feats]
+            agg, _ = torch_port.cost_volume(fs, pm, dev["depth_values"], dev["view_weights"])
+            ref_grads = torch.autograd.grad(agg.squeeze(1), fs, g)
+            fs2 = [f.clone().requires_grad_(True) for f in feats]
+            agg2, _ = ops.cost_volume(fs2[0], fs2[1:], rt, dev["depth_values"], dev["view_weights"])
+            our_grads = torch.autograd.grad(agg2, fs2, g)
+            for v, (a, b) in enumerate(zip(our_grads, ref_grads)):
+                e_max, e_l2 = rel_err(a.cpu().numpy(), b.cpu().numpy())
+                assert e_max <= 1e-4 and e_l2 <= 1e-4, (shape, stage, v, e_max, e_l2)
+        del dev, feats, want, got
+        torch.cuda.empty_cache()
