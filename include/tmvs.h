@@ -73,6 +73,8 @@ typedef void *tmvs_stream_t;
 #define TMVS_F_FWD_SWEEP       0x40u  /* tmvs_costvol_fwd (aggregated output, C = 8 or 16): epipolar-sweep kernel
                                          (tmvs_costvol_sweep.cu) -- bit-identical results, fewer loads where the
                                          hypotheses of a pixel are less than a pixel apart in the source image */
+#define TMVS_F_RAY_UNFUSED     0x80u  /* rot @ (x, y, 1) of models/module.py:305 evaluated as ((r0*x) + (r1*y)) + r2 instead of
+                                         fma(r2, 1, fma(r1, y, r0*x)): what cuBLAS does for the small stage-1 maps (probed) */
 #define TMVS_F_TABLE_MB(mb)    ((unsigned)(mb) << 16)   /* tmvs_costvol_bwd(+_workspace_bytes): cap of the cell-table
                                          workspace in MiB (0 = default 3072), e.g. to exercise the multi-pass path */
 

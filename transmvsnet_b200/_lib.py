@@ -57,6 +57,7 @@ F_BWD_SCAN = 0x8
 F_PACK_LDG = 0x10
 F_FWD_SPLIT = 0x20
 F_FWD_SWEEP = 0x40
+F_RAY_UNFUSED = 0x80
 
 
 def f_table_mb(mb: int) -> int:

@@ -134,7 +134,7 @@ costvol_fwd_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     for (int i = 0; i < n_src; ++i) {
         float rt[12];
         tmvs_geom_rt(geom, i, bl, b_chunk, rt);
-        const TmvsRay ray = tmvs_ray(rt, xf, yf);
+        const TmvsRay ray = tmvs_ray(rt, xf, yf, geom.ray_unfused);
         float tx = rt[9], ty = rt[10], tz = rt[11];
         // opaque to the optimiser: keep them in registers for the depth loop instead of re-deriving them (constant-bank
         // index arithmetic and 64-bit multiplies) once per plane

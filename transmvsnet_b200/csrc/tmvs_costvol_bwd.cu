@@ -67,7 +67,7 @@ bwd_ref_kernel(const float4 *__restrict__ packed, const float *__restrict__ dept
     const size_t HW = (size_t)H * W, pix = (size_t)y * W + x;
     float rt[12];
     tmvs_geom_rt(geom, i, bl, b_chunk, rt);
-    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y, geom.ray_unfused);
     const float inv_c = 1.0f / (float)C;
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
@@ -136,7 +136,7 @@ bwd_bbox_kernel(const float *__restrict__ depth, int4 *__restrict__ bbox, int b_
     const size_t HW = (size_t)H * W, pix = (size_t)min(y, H - 1) * W + min(x, W - 1);
     float rt[12];
     tmvs_geom_rt(geom, i, bl, b_chunk, rt);
-    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y, geom.ray_unfused);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const int tile = blockIdx.y * n_tx + blockIdx.x;
     int4 *out = bbox + ((size_t)blockIdx.z * n_tiles + tile) * D;
@@ -348,7 +348,7 @@ bwd_src_kernel(const float4 *__restrict__ refp, const float *__restrict__ depth,
                     const bool p_valid = px < W && py < H;
                     int my_cell[kPlanes];
                     TmvsRay ray;
-                    if (p_valid) ray = tmvs_ray(rt, (float)px, (float)py);
+                    if (p_valid) ray = tmvs_ray(rt, (float)px, (float)py, geom.ray_unfused);
                     pixrec[tid] = tmvs_pk_off(pk, min(px, W - 1), min(py, H - 1) * pk.row);   // packed word of ref pixel p
 #pragma unroll
                     for (int pl = 0; pl < kPlanes; ++pl) {

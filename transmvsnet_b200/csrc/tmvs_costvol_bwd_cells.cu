@@ -71,7 +71,7 @@ cells_register_kernel(const float *__restrict__ depth, CellTables tb, int z0, in
     const size_t ncell = (size_t)(H + 1) * (W + 1);
     float rt[12];
     tmvs_geom_rt(geom, z / b_chunk, bl, b_chunk, rt);
-    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y, geom.ray_unfused);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const unsigned id = ((unsigned)y << 16) | (unsigned)x;
     const int cls = (x & 1) | ((y & 1) << 1);

@@ -261,7 +261,7 @@ costvol_fwd_sweep_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, 
     for (int i = 0; i < n_src; ++i) {
         float rt[12];
         tmvs_geom_rt(geom, i, bl, b_chunk, rt);
-        const TmvsRay ray = tmvs_ray(rt, xf, yf);
+        const TmvsRay ray = tmvs_ray(rt, xf, yf, geom.ray_unfused);
         float tx = rt[9], ty = rt[10], tz = rt[11];
         asm volatile("" : "+f"(tx), "+f"(ty), "+f"(tz));
         const float wi = __ldg(vw_p + (size_t)i * vw_hw);

@@ -137,7 +137,7 @@ costvol_tma_kernel(const float *__restrict__ ref, int64_t rB, int64_t rC, int64_
     for (int i = 0; i < n_src; ++i) {
         float rt[12];
         tmvs_geom_rt(geom, i, bl, b_chunk, rt);
-        const TmvsRay ray = tmvs_ray(rt, xf, yf);
+        const TmvsRay ray = tmvs_ray(rt, xf, yf, geom.ray_unfused);
         float wi = 0.0f;
         if (AGG) wi = __ldg(vw + ((size_t)b * n_src + i) * HW + pix);
         const float4 *img = packed + ((size_t)i * b_total + b) * pk.slice;     // global path (window too large)

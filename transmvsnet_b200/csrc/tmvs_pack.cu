@@ -121,7 +121,7 @@ homo_warp_fwd_kernel(const float4 *__restrict__ packed, const float *__restrict_
     const size_t pix = (size_t)y * W + x;
     float rt[12];
     tmvs_geom_rt(geom, 0, bl, b_chunk, rt);
-    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y);
+    const TmvsRay ray = tmvs_ray(rt, (float)x, (float)y, geom.ray_unfused);
     const TmvsDims dims = tmvs_dims(H, W, geom.arith);
     const TmvsPacked pk = tmvs_packed_layout(c4, H, W);
     const float4 *img = packed + (size_t)b * pk.slice;

@@ -24,7 +24,7 @@ from .geometry import relative_rot_trans
 # Which of the reference's two fp32 arithmetics the kernels follow is a PER-CALL flag of the C ABI (include/tmvs.h).
 # The ops below run on CUDA tensors, so their default is the arithmetic of the device the reference would have run on:
 # ATen's CUDA kernels ("cuda": `x / ((W-1)/2)` as a reciprocal multiply).  "cpu" follows ATen's CPU kernels (true
-# division) -- what the CPU-generated golden vectors and the C oracle pin.  Every op takes `arith=`; a caller that
+# division) -- what the CPU-generated golden vectors (and the CPU checker of the test suite) pin.  Every op takes `arith=`; a caller that
 # cannot pass it (code under test behind the reference's signatures) scopes it with `reference_arithmetic(...)`,
 # which is context-local (contextvars), not process-wide.  TMVS_ARITH in the environment only seeds that default for
 # test runs; the library itself reads no environment variable.
@@ -54,6 +54,39 @@ def extra_flags(bits: int):
         yield
     finally:
         _EXTRA_FLAGS.reset(tok)
+
+
+# torch.matmul(rot[B,3,3], xyz[B,3,HW]) (models/module.py:305) is a library GEMM whose kernel -- and with it the order in
+# which the K = 3 dot product is evaluated -- depends on the problem size: on B200 / cuBLAS 12 the small stage-1 maps are
+# evaluated UNFUSED, ((r0*x) + (r1*y)) + r2, the larger ones as fma(r2, 1, fma(r1, y, r0*x)) (scripts/probe_matmul.py).
+# To land on the reference's CUDA rays bit for bit at every size, the CUDA arithmetic asks the library itself: one
+# torch.matmul of the call's shape per (device, B, H, W), compared on the host with both candidate orders, cached.
+_RAY_ORDER: dict = {}
+
+
+def _ray_bits(dev: torch.device, b: int, h: int, w: int, arith: Optional[str]) -> int:
+    which = _ARITH.get() if arith is None else arith
+    if which != "cuda":
+        return 0                      # ATen's CPU path (MKL) is fused at every size
+    key = (dev.index, b, h, w)
+    if key not in _RAY_ORDER:
+        import numpy as np
+        with torch.no_grad():
+            rot = torch.tensor([[1.0103, 0.0131, -7.7021], [-0.0113, 0.9907, 5.3009], [1.1e-5, -2.3e-5, 1.0007]],
+                               dtype=torch.float32, device=dev)[None].repeat(b, 1, 1)
+            ys = torch.arange(0, h, dtype=torch.float32, device=dev).view(h, 1).expand(h, w).reshape(-1)
+            xs = torch.arange(0, w, dtype=torch.float32, device=dev).view(1, w).expand(h, w).reshape(-1)
+            xyz = torch.stack((xs, ys, torch.ones_like(xs)))[None].repeat(b, 1, 1)
+            got = torch.matmul(rot, xyz)[0]                                       # [3, HW], the library's answer
+            idx = torch.linspace(0, h * w - 1, min(h * w, 8192), device=dev).long()
+            got = got[:, idx].cpu().numpy()
+            x, y = xs[idx].cpu().numpy().astype(np.float64), ys[idx].cpu().numpy().astype(np.float64)
+            r = rot[0].cpu().numpy().astype(np.float64)
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)      # products of fp32 values are exact in fp64
+        fused = np.stack([f32(f32(r[k, 1] * y + f32(r[k, 0] * x)) + r[k, 2]) for k in range(3)]).astype(np.float32)
+        unfused = np.stack([f32(f32(f32(r[k, 0] * x) + f32(r[k, 1] * y)) + r[k, 2]) for k in range(3)]).astype(np.float32)
+        _RAY_ORDER[key] = bool((unfused == got).all() and not (fused == got).all())
+    return _lib.F_RAY_UNFUSED if _RAY_ORDER[key] else 0
 
 
 def _flags(arith: Optional[str] = None, extra: int = 0) -> int:
@@ -164,7 +197,8 @@ def homo_warp_packed(packed_view: torch.Tensor, rot_trans, depth_values: torch.T
     out = torch.empty((b, channels, d, h, w), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.tmvs_homo_warp_fwd(_ptr(packed_view), ctypes.c_void_p(rt.data_ptr()), _ptr(depth_values), mode,
-                                    _ptr(out), b, channels, d, h, w, _flags(arith, rt_flag), _stream())
+                                    _ptr(out), b, channels, d, h, w,
+                                    _flags(arith, rt_flag | _ray_bits(dev, b, h, w, arith)), _stream())
     _lib.check(rc, "tmvs_homo_warp_fwd")
     return out
 
@@ -203,7 +237,8 @@ def homo_warp_backward(rot_trans, depth_values: torch.Tensor, grad_out: torch.Te
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.tmvs_homo_warp_bwd(ctypes.c_void_p(rt.data_ptr()), _ptr(depth_values), mode, _ptr(grad_out), _ptr(gsrc),
-                                    _ptr(ws), ws_bytes, b, c, d, h, w, _flags(arith, rt_flag), _stream())
+                                    _ptr(ws), ws_bytes, b, c, d, h, w,
+                                    _flags(arith, rt_flag | _ray_bits(dev, b, h, w, arith)), _stream())
     _lib.check(rc, "tmvs_homo_warp_bwd")
     return gsrc
 
@@ -268,7 +303,7 @@ def cost_volume_packed(ref_fea: torch.Tensor, packed, rot_trans, depth_values: t
     views = torch.empty((n, b, d, h, w), dtype=torch.float32, device=dev) if want_views else None
     agg = torch.empty((b, d, h, w), dtype=torch.float32, device=dev) if want_agg else None
     rb, rc_, rh, rw = ref_fea.stride()
-    flags = _flags(arith, rt_flag)
+    flags = _flags(arith, rt_flag | _ray_bits(dev, b, h, w, arith))
     with torch.cuda.device(dev):
         if per_view or vw_shift:
             ptrs = (ctypes.c_void_p * n)(*[(packed[i] if per_view else packed[i]).data_ptr() for i in range(n)])
@@ -427,7 +462,7 @@ def costvol_backward_packed(ref_fea: torch.Tensor, packed: torch.Tensor, rot_tra
     mode = _depth_mode(depth_values, b, h, w)
     depth_values, grad_views = depth_values.contiguous(), grad_views.contiguous()
     rt, rt_flag = _rt_arg(rot_trans, (n, b, 12), dev)
-    flags = _flags(arith, rt_flag | extra)
+    flags = _flags(arith, rt_flag | extra | _ray_bits(dev, b, h, w, arith))
     gref = torch.empty((b, c, h, w), dtype=torch.float32, device=dev) if need_ref else None
     gsrc = torch.empty((n, b, c, h, w), dtype=torch.float32, device=dev) if need_src else None
     ws_bytes = lib.tmvs_costvol_bwd_workspace_bytes(b, c, d, h, w, n, flags)
