@@ -206,16 +206,17 @@ int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float
  * SURVEY.md 8(f) N4 -- fusibile depth-map fusion (gipuma/fusibile/fusibile.cu:89-173 kernel `fusibile`, :175-210
  * copy_pc_to_host, :216-285 the per-camera launch / synchronise / host-scan loop; main.cpp:128-147 image set-up).
  *   images  [V][H][W][4] fp32: b, g, r in [0,1] and w = depth (425 + 512 * alpha/255, main.cpp:137); sampled through
- *           the texture unit with the reference's settings (float4 cudaArray per view, bilinear, unnormalised + 0.5:
- *           main.cpp:30-66 -- each view is copied into an array this call allocates and frees).  16-byte aligned.
+ *           the texture unit with the reference's settings (float4 texels, bilinear, unnormalised + 0.5: main.cpp:30-66).
+ *           16-byte aligned.  If the buffer is 512-byte aligned, W even and H*W a multiple of 32, the textures are
+ *           built over it in place (pitch-linear resources); otherwise, or with TMVS_FUSE_ARRAY_TEXTURES, each view is
+ *           copied into a cudaArray this call allocates and frees, as the reference does.  Identical samples either way.
  *   cams    HOST [V][TMVS_FUSE_CAM_FLOATS]: P (3x4 row major), RK_inv = inverse(P[:, :3]) (3x3), camera centre C (3),
  *           P[:, 3] (3), focal length K[0] of the decomposed P (cameraGeometryUtils.h:104-156).
  *   depth_threshold 0.25, consistent_threshold 3 (algorithmparameters.h:11-12).
  *   carry_over bit 0 set reproduces the reference's output exactly: its per-pixel point buffer is never cleared between
  *           cameras, so every later camera re-emits a pixel's latest fused point (fusibile.cu:165-166,188);
- *           clear: each camera's own points only.  Bit 1 (TMVS_FUSE_PITCH_LINEAR): sample pitch-linear textures over the
- *           caller's buffer instead (no copy; needs 512-byte alignment, W even, H*W a multiple of 32).  The texture
- *           two resource types give identical samples on B200).  Bit 2 (TMVS_FUSE_IEEE): IEEE division and square root.
+ *           clear: each camera's own points only.  Bit 1 (TMVS_FUSE_ARRAY_TEXTURES): force the cudaArray textures.
+ *           Bit 2 (TMVS_FUSE_IEEE): IEEE division and square root.
  *           The default arithmetic is the reference's AS ITS OWN BUILD COMPILES IT (CMakeLists.txt:10 --use_fast_math:
  *           reciprocal-multiply divisions, MUFU.SQRT, the compiler's FMA contraction order), read off the SASS of
  *           gipuma/fusibile/fusibile.cu; TMVS_FUSE_IEEE is the same source without --use_fast_math.  Both are pinned
@@ -227,7 +228,7 @@ int tmvs_pixelwise_aggregate_fwd(const float *sim_views, const float *mlp, float
  */
 #define TMVS_FUSE_CAM_FLOATS 28
 #define TMVS_FUSE_MAX_VIEWS 1024       /* config.h:2 MAX_IMAGES */
-#define TMVS_FUSE_PITCH_LINEAR 2
+#define TMVS_FUSE_ARRAY_TEXTURES 2
 #define TMVS_FUSE_IEEE 4
 int tmvs_fusibile_fwd(const float *images, const float *cams, int V, int H, int W, float depth_threshold,
                       int consistent_threshold, int carry_over, float *points, long long capacity,
@@ -237,7 +238,7 @@ size_t tmvs_fusibile_workspace_bytes(int V, int H, int W);
  * uv [n][2] unnormalised texture coordinates, out [n][4], all device).  The tests use it to measure the CPU oracle's
  * emulation of the hardware's 9-bit-weight bilinear filter.  Synchronises `stream`. */
 int tmvs_fusibile_tex_probe(const float *image, int H, int W, const float *uv, float *out, int n, int mode,
-                            tmvs_stream_t stream);      /* mode: 0 = array texture, TMVS_FUSE_PITCH_LINEAR */
+                            tmvs_stream_t stream);      /* mode: 0 = pitch-linear texture, TMVS_FUSE_ARRAY_TEXTURES */
 
 /*
  * Backward of the cost volume wrt the features (autograd of models/module.py:318-320 and

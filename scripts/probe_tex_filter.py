@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transmvsnet_b200 import _lib  # noqa: E402
 
 DEV = torch.device("cuda:0")
-MODE = 2 if "--pitch-linear" in sys.argv else 0       # 0: cudaArray texture (the reference's), 2: pitch-linear
+MODE = 2 if "--array" in sys.argv else 0       # 0: pitch-linear texture over the buffer, 2: cudaArray texture (the reference's)
 h, w = 32, 64
 img = torch.zeros(h, w, 4)
 img[..., 0] = torch.arange(w)[None, :].float()
@@ -49,6 +49,6 @@ for ch in (2, 3):
 res["n"] = n
 print(json.dumps(res))
 os.makedirs("gpurun_out", exist_ok=True)
-res["texture"] = "pitch-linear" if MODE else "cudaArray"
+res["texture"] = "cudaArray" if MODE else "pitch-linear"
 json.dump(res, open(f"gpurun_out/probe_tex_{'pitch' if MODE else 'array'}.json", "w"), indent=1)
 np.savez(f"gpurun_out/probe_tex_{'pitch' if MODE else 'array'}.npz", img=img.cpu().numpy(), uv=uv, out=out.cpu().numpy())

@@ -64,12 +64,13 @@ def images_from_bgra(bgra_u8: torch.Tensor) -> torch.Tensor:
 
 
 def fuse_depth_maps(images: torch.Tensor, cams, depth_threshold: float = 0.25, consistent_threshold: int = 3,
-                    carry_over: bool = True, capacity: int | None = None, pitch_linear: bool = False, ieee: bool = False) -> torch.Tensor:
+                    carry_over: bool = True, capacity: int | None = None, array_textures: bool = False, ieee: bool = False) -> torch.Tensor:
     """images [V,H,W,4] fp32 CUDA (b, g, r, depth), cams [V,28] (camera_records) -> fused points [n,8]
     (x, y, z, 0, b, g, r, 0) in the reference's order.  carry_over=True reproduces the reference's output, including
     the points every later camera re-emits because the per-pixel buffer is never cleared (fusibile.cu:165-166,188).
-    pitch_linear=True samples pitch-linear textures over `images` itself (no copy into arrays) at the price of the
-    512-byte alignment pitch-linear textures need.  ieee=True: the reference's source compiled WITHOUT its
+    The images are sampled in place through pitch-linear textures when the buffer allows it (512-byte aligned, W even,
+    H*W a multiple of 32), else -- or with array_textures=True -- through one cudaArray per view like the reference;
+    both give the same samples.  ieee=True: the reference's source compiled WITHOUT its
     --use_fast_math flag (IEEE division / square root); the default mirrors the reference's own build."""
     lib = _lib.load()
     if not images.is_cuda:
@@ -91,7 +92,7 @@ def fuse_depth_maps(images: torch.Tensor, cams, depth_threshold: float = 0.25, c
     with torch.cuda.device(dev):
         rc = lib.tmvs_fusibile_fwd(ctypes.c_void_p(images.data_ptr()), ctypes.c_void_p(cams_h.data_ptr()), v, h, w,
                                    float(depth_threshold), int(consistent_threshold),
-                                   int(bool(carry_over)) | (2 if pitch_linear else 0) | (4 if ieee else 0),
+                                   int(bool(carry_over)) | (2 if array_textures else 0) | (4 if ieee else 0),
                                    ctypes.c_void_p(points.data_ptr()), int(capacity), ctypes.c_void_p(count.data_ptr()),
                                    ctypes.c_void_p(ws.data_ptr()), ws_bytes,
                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
