@@ -8,7 +8,8 @@ the three stages  pack sources -> fused cost volume (warp+sample+correlate+aggre
 read-out  = 9 kernel launches.  metric = cost-volume voxel-views/s (D*h*w*Nsrc summed over the stages,
 BASELINE.json) and ms per reference view.  Under torchrun every rank processes its own reference
 views (weak scaling, sharded by reference view) and the stage-3 depth/confidence maps are gathered
-on rank 0 over NCCL.
+on rank 0: by default the read-out kernel stores them straight into rank 0's peer-mapped buffer over
+NVLink (TMVS_GATHER=peer); TMVS_GATHER=copy uses the copy engine, TMVS_GATHER=nccl an NCCL all_gather.
 
 --impl reference times the REFERENCE's own function for the path -- models.TransMVSNet.DepthNet.forward of the
 unmodified model package staged under oracle/_ref by build() (oracle/build.py; /root/reference does not exist on the
