@@ -14,9 +14,8 @@ from transmvsnet_b200 import build  # noqa: E402
 OUT = os.path.join(REPO, "build", "variants")
 VARIANTS = {
     "base": {},
-    "gather244": {"TMVS_GATHER_MINB4": 4, "TMVS_GATHER_MINB2": 4},
-    "gather245_ref245": {"TMVS_GATHER_MINB4": 4, "TMVS_GATHER_MINB2": 5, "TMVS_BWDREF_MINB4": 4, "TMVS_BWDREF_MINB2": 5},
-    "ref222": {"TMVS_BWDREF_MINB4": 2, "TMVS_BWDREF_MINB2": 2},
+    "pf1": {"TMVS_GATHER_PF": 1},
+    "pf2": {"TMVS_GATHER_PF": 2},
 }
 
 
@@ -39,8 +38,9 @@ def build_all():
 
 def time_all(which):
     rows = []
-    for tag in VARIANTS:
-        lib = os.path.join(OUT, f"libtmvs_{tag}.so")
+    order = os.environ.get("TUNE_ORDER")
+    for tag in (order.split(",") if order else VARIANTS):
+        lib = os.path.join(OUT, f"libtmvs_{tag.split('@')[0]}.so")
         if not os.path.exists(lib):
             continue
         res = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "time_bwd.py"), which],
@@ -48,7 +48,7 @@ def time_all(which):
         line = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-300:]
         print(tag, line, flush=True)
         try:
-            rows.append({"variant": tag, "defs": VARIANTS[tag], **json.loads(line)})
+            rows.append({"variant": tag, "defs": VARIANTS.get(tag.split("@")[0], {}), **json.loads(line)})
         except ValueError:
             pass
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)

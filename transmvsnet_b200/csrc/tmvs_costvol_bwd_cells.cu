@@ -203,6 +203,19 @@ cells_fixup_list_kernel(CellTables tb, int D, int H, int W)
     }
 }
 
+// The gather walks D planes of tables that are far larger than L2; every plane costs three dependent trips through
+// the memory system (cell -> position / gradient of the registrant -> reference features).  The cell addresses of the
+// next plane are known in advance and its registrants sit next to this plane's, so both are requested from L2 one
+// plane ahead (CCTL.E.PF2, no registers).  Measured (profiles/r2_tune_bwd_prefetch_*.json): 2 = cells + registrants
+// -1.9 / -1.5 / -2.3 % per grad_src call at DTU size, 1 = cells only +-0, two planes ahead slower; 0 = off.
+#ifndef TMVS_GATHER_PF
+#define TMVS_GATHER_PF 2
+#endif
+#ifndef TMVS_GATHER_PFD
+#define TMVS_GATHER_PFD 1                       // planes ahead
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void cswap_u(unsigned &a, unsigned &b)
 {
     const unsigned lo = min(a, b), hi = max(a, b);
@@ -260,6 +273,15 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
     for (int g = 0; g < C4T; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int d = 0; d < D; ++d, par_d += ncell, ovf_d += ncell, pos_d += HW, g_d += HW) {
+        if (TMVS_GATHER_PF >= 1 && d + TMVS_GATHER_PFD < D) {   // a later plane's cells (class 1 / 3 share the lines of 0 / 2)
+            const size_t ahead = (size_t)TMVS_GATHER_PFD * ncell;
+            prefetch_l2(par_d + ahead + c0);
+            prefetch_l2(par_d + ahead + c0 - wp1);
+            if (has_ovf) {
+                prefetch_l2(ovf_d + ahead + c0);
+                prefetch_l2(ovf_d + ahead + c0 - wp1);
+            }
+        }
         // ids of every class in ascending order (empties last)
         unsigned ids[4][6];
 #pragma unroll
@@ -285,6 +307,14 @@ cells_gather_kernel(const float4 *__restrict__ refp, const float *__restrict__ G
                 cswap_u(v[1], v[2]); cswap_u(v[3], v[4]);
             } else {
                 cswap_u(v[0], v[1]); cswap_u(v[2], v[3]); cswap_u(v[0], v[2]); cswap_u(v[1], v[3]); cswap_u(v[1], v[2]);
+            }
+        }
+        if (TMVS_GATHER_PF >= 2 && d + 1 < D) {             // next plane's registrants are this plane's neighbours
+            const unsigned id = min(min(ids[0][0], ids[1][0]), min(ids[2][0], ids[3][0]));
+            if (id != kEmptyId) {
+                const unsigned pix = (id >> 16) * (unsigned)W + (id & 0xffffu);
+                prefetch_l2(pos_d + HW + pix);
+                prefetch_l2(g_d + HW + pix);
             }
         }
 #pragma unroll
