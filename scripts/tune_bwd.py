@@ -13,9 +13,10 @@ from transmvsnet_b200 import build  # noqa: E402
 
 OUT = os.path.join(REPO, "build", "variants")
 VARIANTS = {
-    "base": {},
+    "base": {},                                   # TMVS_GATHER_PF defaults to 2 (cells + registrants one plane ahead)
+    "pf0": {"TMVS_GATHER_PF": 0},
     "pf1": {"TMVS_GATHER_PF": 1},
-    "pf2": {"TMVS_GATHER_PF": 2},
+    "pf1d2": {"TMVS_GATHER_PF": 1, "TMVS_GATHER_PFD": 2},
 }
 
 
